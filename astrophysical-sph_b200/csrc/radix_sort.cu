@@ -1,0 +1,247 @@
+// radix_sort.cu -- CUB-free stable LSD radix sort of (u64 key, i32 value) pairs and a device-wide
+// exclusive scan, both hand-written for sm_100a.
+//
+// Replaces the implicit grouping of particles by octant in addNodes! (F/gravOctree_Single.jl:151-156;
+// the reference re-buckets the particle list of every node it subdivides) and the KD-tree build of
+// NearestNeighbors.jl (F/isothermal_hydroKDTree.jl:128): one sort by 63-bit octant path key orders the
+// particles so that EVERY octree cell of every level is a contiguous range.
+//
+// Pass structure (8 bits per pass, tile = 256 threads x 16 keys):
+//   hist    per-tile digit histogram           -> ghist[digit][tile]
+//   scan    exclusive scan of ghist (digit-major, so the scan yields global start offsets)
+//   scatter stable in-tile ranking with __match_any_sync + per-warp digit counters, then scatter
+// HBM traffic per pass: 2 reads + 1 write of 12 B per element.
+#include "sph_internal.cuh"
+
+namespace {
+
+constexpr int RS_BITS = 8;
+constexpr int RS_BINS = 1 << RS_BITS;
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+constexpr int SC_THREADS = 512;
+constexpr int SC_ITEMS = 8;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
+
+__device__ __forceinline__ int64_t eff_n(int64_t n, const unsigned long long *n_dev) {
+    return n_dev ? min((int64_t)*n_dev, n) : n;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n_cap,
+                                                              const unsigned long long *n_dev, int shift,
+                                                              int *__restrict__ ghist, int ntiles) {
+    __shared__ int hist[RS_BINS];
+    const int64_t n = eff_n(n_cap, n_dev);
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; ++it) {
+        const int64_t e = base + it * RS_THREADS + threadIdx.x;
+        if (e < n) atomicAdd(&hist[(int)((keys[e] >> shift) & (RS_BINS - 1))], 1);
+    }
+    __syncthreads();
+    ghist[(int64_t)threadIdx.x * ntiles + blockIdx.x] = hist[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *__restrict__ keys_in,
+                                                                 const int *__restrict__ vals_in,
+                                                                 uint64_t *__restrict__ keys_out,
+                                                                 int *__restrict__ vals_out, int64_t n_cap,
+                                                                 const unsigned long long *n_dev, int shift,
+                                                                 const int *__restrict__ goff, int ntiles) {
+    __shared__ int cnt[RS_WARPS][RS_BINS];
+    const int64_t n = eff_n(n_cap, n_dev);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    // warp w owns the contiguous slice [base + w*512, base + (w+1)*512), visited in 16 rounds of 32
+    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_ITEMS);
+    uint64_t key[RS_ITEMS];
+    int rank[RS_ITEMS];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; ++it) {
+        const int64_t e = wbase + it * 32 + lane;
+        const bool ok = e < n;
+        key[it] = ok ? keys_in[e] : 0ull;
+        // invalid lanes get a private pseudo-digit so they never join a valid group
+        const unsigned dig = ok ? (unsigned)((key[it] >> shift) & (RS_BINS - 1)) : (0x10000u + lane);
+        const unsigned grp = __match_any_sync(0xffffffffu, dig);
+        const int leader = __ffs(grp) - 1;
+        int pre = 0;
+        if (ok && lane == leader) {
+            pre = cnt[warp][dig];
+            cnt[warp][dig] = pre + __popc(grp);
+        }
+        pre = __shfl_sync(0xffffffffu, pre, leader);
+        rank[it] = pre + __popc(grp & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // thread d: turn the per-warp counts of digit d into start offsets (global base + earlier warps)
+        const int d = threadIdx.x;
+        int run = goff[(int64_t)d * ntiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const int c = cnt[w][d];
+            cnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; ++it) {
+        const int64_t e = wbase + it * 32 + lane;
+        if (e < n) {
+            const unsigned dig = (unsigned)((key[it] >> shift) & (RS_BINS - 1));
+            const int dst = cnt[warp][dig] + rank[it];
+            keys_out[dst] = key[it];
+            vals_out[dst] = vals_in[e];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- scan (three phases)
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total, int *smem /* >= 32 ints */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nw ? smem[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        smem[lane] = winc - w;  // exclusive offset of each warp
+        if (lane == 31) smem[32] = winc;
+    }
+    __syncthreads();
+    const int res = smem[warp] + inc - v;
+    if (total) *total = smem[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) scan_tile_sums(const int *__restrict__ in, int64_t n,
+                                                              int *__restrict__ tile_sum) {
+    __shared__ int sm[40];
+    const int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k)
+        if (base + k < n) s += in[base + k];
+    int tot;
+    block_exclusive_scan(s, &tot, sm);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of the tile sums in place; also writes the grand total to tile_sum[ntiles]
+__global__ void __launch_bounds__(1024) scan_of_sums(int *tile_sum, int ntiles) {
+    __shared__ int sm[40];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b = 0; b < ntiles; b += 1024) {
+        const int i = b + threadIdx.x;
+        const int v = i < ntiles ? tile_sum[i] : 0;
+        int tot;
+        const int ex = block_exclusive_scan(v, &tot, sm);
+        if (i < ntiles) tile_sum[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sum[ntiles] = carry;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) scan_apply(const int *__restrict__ in, int *__restrict__ out, int64_t n,
+                                                          const int *__restrict__ tile_sum, int ntiles) {
+    __shared__ int sm[40];
+    const int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
+    int v[SC_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    int run = block_exclusive_scan(s, nullptr, sm) + tile_sum[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = tile_sum[ntiles];
+}
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace
+
+size_t sph_sort_temp_bytes(int64_t n) {
+    const int64_t ntiles = cdiv(n, RS_TILE);
+    const int64_t hist = (int64_t)RS_BINS * ntiles;
+    const int64_t scan_tiles_hist = cdiv(hist, SC_TILE);
+    const int64_t scan_tiles_n = cdiv(n + 1, SC_TILE);
+    const int64_t st = scan_tiles_hist > scan_tiles_n ? scan_tiles_hist : scan_tiles_n;
+    return align256((size_t)(hist + 1) * 4) * 2 + align256((size_t)(st + 2) * 4) + 1024;
+}
+
+cudaError_t sph_exclusive_scan(const int *in, int *out, int64_t n, void *temp, size_t temp_bytes, cudaStream_t st) {
+    const int ntiles = (int)cdiv(n, SC_TILE);
+    if ((size_t)(ntiles + 2) * 4 > temp_bytes) return cudaErrorInvalidValue;
+    int *tile_sum = (int *)temp;
+    scan_tile_sums<<<ntiles, SC_THREADS, 0, st>>>(in, n, tile_sum);
+    scan_of_sums<<<1, 1024, 0, st>>>(tile_sum, ntiles);
+    scan_apply<<<ntiles, SC_THREADS, 0, st>>>(in, out, n, tile_sum, ntiles);
+    return cudaGetLastError();
+}
+
+cudaError_t sph_sort_pairs(uint64_t *keys_in, int *vals_in, uint64_t *keys_out, int *vals_out, int64_t n,
+                           const unsigned long long *n_dev, int begin_bit, int end_bit, void *temp,
+                           size_t temp_bytes, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (temp_bytes < sph_sort_temp_bytes(n)) return cudaErrorInvalidValue;
+    const int ntiles = (int)cdiv(n, RS_TILE);
+    const int64_t hist = (int64_t)RS_BINS * ntiles;
+    char *tp = (char *)temp;
+    int *ghist = (int *)tp;
+    tp += align256((size_t)(hist + 1) * 4);
+    int *goff = (int *)tp;
+    tp += align256((size_t)(hist + 1) * 4);
+    void *scan_tmp = tp;
+    const size_t scan_tmp_bytes = temp_bytes - (size_t)(tp - (char *)temp);
+
+    const int npass = (end_bit - begin_bit + RS_BITS - 1) / RS_BITS;
+    // an even number of ping-pongs would leave the result in *_in: copy instead of constraining callers
+    uint64_t *ka = keys_in, *kb = keys_out;
+    int *va = vals_in, *vb = vals_out;
+    for (int p = 0; p < npass; ++p) {
+        const int shift = begin_bit + p * RS_BITS;
+        rs_hist_kernel<<<ntiles, RS_THREADS, 0, st>>>(ka, n, n_dev, shift, ghist, ntiles);
+        cudaError_t e = sph_exclusive_scan(ghist, goff, hist, scan_tmp, scan_tmp_bytes, st);
+        if (e != cudaSuccess) return e;
+        rs_scatter_kernel<<<ntiles, RS_THREADS, 0, st>>>(ka, va, kb, vb, n, n_dev, shift, goff, ntiles);
+        uint64_t *tk = ka; ka = kb; kb = tk;
+        int *tv = va; va = vb; vb = tv;
+    }
+    if (ka != keys_out) {  // result currently in keys_in/vals_in
+        cudaMemcpyAsync(keys_out, ka, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(vals_out, va, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+    }
+    return cudaGetLastError();
+}

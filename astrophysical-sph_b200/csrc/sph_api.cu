@@ -1,0 +1,604 @@
+// sph_api.cu -- the C ABI of libsph_b200.so (include/sph_b200.h): handle lifecycle, one force
+// evaluation (= getAcc, F/isothermal_sim.jl:16-49 / F/polytrope_sim.jl:17-51), the stepping loop
+// (F/isothermal_sim.jl:152-213 / F/polytrope_sim.jl:158-232), inspection getters and the NCCL plumbing.
+//
+// There is no CPU path in this library: without an sm_100 device sph_create fails with SPH_ERR_NO_DEVICE.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "sph_internal.cuh"
+
+namespace {
+
+std::string g_create_err;
+
+// ---- NCCL, bound lazily so that the library loads (and the single-GPU path runs) without it ------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+NcclApi &nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // RTLD_NOLOAD first: inside a torch process this is torch's bundled libnccl.so.2
+        api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!api.lib) api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.lib) { api.why = std::string("dlopen libnccl.so.2: ") + dlerror(); return; }
+#define BIND(name)                                                                   \
+        *(void **)(&api.name) = dlsym(api.lib, "nccl" #name);                        \
+        if (!api.name) { api.why = "missing symbol nccl" #name; return; }
+        BIND(GetUniqueId) BIND(CommInitRank) BIND(CommDestroy) BIND(AllGather) BIND(AllReduce)
+        BIND(GroupStart) BIND(GroupEnd) BIND(GetErrorString)
+#undef BIND
+        api.ok = true;
+    });
+    return api;
+}
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t n) {
+    return cudaMalloc((void **)p, n * sizeof(T) + 256);
+}
+
+__global__ void sticky_kernel(unsigned long long *scal) { scal[SC_STICKY] |= scal[SC_ERR]; }
+
+__global__ void export_nbr_kernel(int64_t N, int K, const int *__restrict__ perm, const int *__restrict__ nbr,
+                                  const double4 *__restrict__ pos4, int *__restrict__ idx_out,
+                                  double *__restrict__ r_out) {
+    const int64_t tot = N * (int64_t)K;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = e % N, j = e / N;
+        const int nj = nbr[e];
+        const int64_t i = perm[s];
+        if (idx_out) idx_out[i + j * N] = perm[nj] + 1;  // 1-based, caller's particle ids
+        if (r_out) {
+            const double4 a = pos4[s], b = pos4[nj];
+            r_out[i + j * N] = sqrt(sph_d2_exact(a.x - b.x, a.y - b.y, a.z - b.z));
+        }
+    }
+}
+
+__global__ void export_tree_kernel(SphTree t, const unsigned long long *__restrict__ scal, double m, int64_t cap,
+                                   double *__restrict__ out) {
+    const int64_t M = min((int64_t)scal[SC_NNODES], cap);
+    const double l = __longlong_as_double((long long)scal[SC_LDOM]);
+    (void)l;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < M; k += (int64_t)gridDim.x * blockDim.x) {
+        const double4 A = t.nodeA[k], B = t.nodeB[k], C = t.nodeC[k];
+        const int2 I = t.nodeI[k];
+        double *o = out + 16 * k;
+        o[0] = C.w;
+        // centre: midpoint is NOT how the reference defines it; recover it from the stored recurrence
+        o[4] = B.x; o[5] = B.y; o[6] = B.z; o[7] = B.w; o[8] = C.x; o[9] = C.y;
+        o[10] = I.y == 0 ? m : A.w;
+        o[11] = A.x; o[12] = A.y; o[13] = A.z;
+        o[14] = k == 0 ? 0.0 : (double)t.ncount[k];  // the reference's root keeps particle_count = 0 (:94-104)
+        o[15] = (double)t.ndepth[k];
+    }
+}
+
+__global__ void export_tree_centres_kernel(SphTree t, const unsigned long long *__restrict__ scal,
+                                           const uint64_t *__restrict__ keys, int64_t cap, double *__restrict__ out) {
+    const int64_t M = min((int64_t)scal[SC_NNODES], cap);
+    const double l = __longlong_as_double((long long)scal[SC_LDOM]);
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < M; k += (int64_t)gridDim.x * blockDim.x) {
+        const SphCell g = sph_cell_of(keys[t.nstart[k]], t.ndepth[k], l);
+        out[16 * k + 1] = g.c[0]; out[16 * k + 2] = g.c[1]; out[16 * k + 3] = g.c[2];
+    }
+}
+
+int check_flags(sph_handle *h) {
+    // copies the device scalars and turns sticky error flags into a status
+    if (cudaMemcpyAsync(h->h_scal, h->scal, sizeof(unsigned long long) * SC_COUNT, cudaMemcpyDeviceToHost,
+                        h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess)
+        return sph_fail(h, SPH_ERR_CUDA, std::string("device error: ") + cudaGetErrorString(cudaGetLastError()));
+    const unsigned long long f = h->h_scal[SC_STICKY] | h->h_scal[SC_ERR];
+    if (f) {
+        cudaMemsetAsync(h->scal + SC_STICKY, 0, sizeof(unsigned long long), h->stream);
+        if (f & ERRF_DEPTH)
+            return sph_fail(h, SPH_ERR_TREE_DEPTH,
+                            "octree: two particles share all 21 octant levels (coincident particles?); the "
+                            "reference's build_octree! does not terminate on such input");
+        if (f & ERRF_NODES) return sph_fail(h, SPH_ERR_TREE_NODES, "octree: node pool exhausted (set SPH_B200_NODE_FACTOR)");
+        return sph_fail(h, SPH_ERR_CUDA, "tree walk stack overflow");
+    }
+    return SPH_OK;
+}
+
+int nccl_fail(sph_handle *h, ncclResult_t r, const char *what) {
+    return sph_fail(h, SPH_ERR_NCCL, std::string(what) + ": " + nccl_api().GetErrorString(r));
+}
+#define SPH_NCCL(h, call)                                   \
+    do {                                                    \
+        ncclResult_t r__ = (call);                          \
+        if (r__ != ncclSuccess) return nccl_fail((h), r__, #call); \
+    } while (0)
+
+// One getAcc on device arrays in the caller's particle order.
+int eval_internal(sph_handle *h, const double *pos, const double *vel, const double *kent, double *acc_out) {
+    cudaStream_t st = h->stream;
+    const int64_t N = h->N;
+    const bool multi = h->nranks > 1;
+    const int64_t chunk = h->NS / h->nranks;
+    int64_t t0 = (int64_t)h->rank * chunk, t1 = t0 + chunk;
+    if (t0 > N) t0 = N;
+    if (t1 > N) t1 = N;
+    NcclApi &nc = nccl_api();
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+
+    SPH_CUDA(h, cudaEventRecord(h->ev[0], st));
+    SPH_CUDA(h, sph_launch_domain_keys(h, pos));
+    SPH_CUDA(h, sph_launch_permute(h, pos, vel, kent));
+    SPH_CUDA(h, cudaEventRecord(h->ev[PH_SORT + 1], st));
+    SPH_CUDA(h, sph_launch_tree(h));
+    SPH_CUDA(h, cudaEventRecord(h->ev[PH_TREE + 1], st));
+    SPH_CUDA(h, sph_launch_knn(h, t0, t1));
+    SPH_CUDA(h, cudaEventRecord(h->ev[PH_KNN + 1], st));
+    SPH_CUDA(h, sph_launch_density(h, t0, t1));
+    if (multi)  // every rank needs h and rho of all particles (neighbours of its targets, leaf softening)
+        SPH_NCCL(h, nc.AllGather(h->hr + h->rank * chunk, h->hr, (size_t)chunk * 2, ncclDouble, comm, st));
+    SPH_CUDA(h, sph_launch_eos(h));
+    SPH_CUDA(h, cudaEventRecord(h->ev[PH_DENSITY + 1], st));
+    SPH_CUDA(h, sph_launch_force(h, t0, t1));
+    if (multi) {
+        // reactions a_j += ct*gradW land on particles of other ranks: sum the partial accelerations
+        SPH_NCCL(h, nc.GroupStart());
+        SPH_NCCL(h, nc.AllReduce(h->s_ahyd, h->s_ahyd, (size_t)h->NS * 3, ncclDouble, ncclSum, comm, st));
+        SPH_NCCL(h, nc.AllReduce(h->s_dkdt, h->s_dkdt, (size_t)h->NS, ncclDouble, ncclSum, comm, st));
+        SPH_NCCL(h, nc.AllGather(h->s_sumvdw + h->rank * chunk, h->s_sumvdw, (size_t)chunk, ncclDouble, comm, st));
+        SPH_NCCL(h, nc.AllGather(h->s_mumax + h->rank * chunk, h->s_mumax, (size_t)chunk, ncclDouble, comm, st));
+        SPH_NCCL(h, nc.GroupEnd());
+    }
+    SPH_CUDA(h, cudaEventRecord(h->ev[PH_FORCE + 1], st));
+    SPH_CUDA(h, sph_launch_walk(h, t0, t1));
+    if (multi) {
+        SPH_NCCL(h, nc.GroupStart());
+        for (int k = 0; k < 3; ++k)
+            SPH_NCCL(h, nc.AllGather(h->s_g + k * h->NS + h->rank * chunk, h->s_g + k * h->NS, (size_t)chunk,
+                                     ncclDouble, comm, st));
+        SPH_NCCL(h, nc.AllGather(h->s_phi + h->rank * chunk, h->s_phi, (size_t)chunk, ncclDouble, comm, st));
+        SPH_NCCL(h, nc.GroupEnd());
+    }
+    SPH_CUDA(h, cudaEventRecord(h->ev[PH_GRAV + 1], st));
+    SPH_CUDA(h, sph_launch_finish(h, acc_out));
+    sticky_kernel<<<1, 1, 0, st>>>(h->scal);
+    SPH_CUDA(h, cudaEventRecord(h->ev[PH_FINISH + 1], st));
+    h->ev_valid = true;
+    h->have_eval = true;
+    h->lists_valid = true;
+    h->last_acc = acc_out;
+    return SPH_OK;
+}
+
+int d2h(sph_handle *h, double *dst, const double *src, size_t n) {
+    if (!dst) return SPH_OK;
+    SPH_CUDA(h, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return SPH_OK;
+}
+
+}  // namespace
+
+int sph_fail(sph_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+
+extern "C" {
+
+int sph_abi_version(void) { return SPH_B200_ABI_VERSION; }
+
+int sph_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *sph_last_error(const sph_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int sph_create(const sph_params *p, sph_handle **out) {
+    if (!p || !out) return sph_fail(nullptr, SPH_ERR_INVALID, "sph_create: null argument");
+    *out = nullptr;
+    if (p->N < 64 || p->N > 0x7fffff00LL / 4) return sph_fail(nullptr, SPH_ERR_INVALID, "sph_create: N must be in [64, 2^29)");
+    if (p->Kh < 2 || p->Kh > 224 || p->Kh > p->N) return sph_fail(nullptr, SPH_ERR_INVALID, "sph_create: Kh must be in [2, min(N,224)]");
+    if (p->eos != SPH_EOS_ISOTHERMAL && p->eos != SPH_EOS_POLYTROPIC)
+        return sph_fail(nullptr, SPH_ERR_INVALID, "sph_create: unknown EOS");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return sph_fail(nullptr, SPH_ERR_NO_DEVICE, "sph_create: no CUDA device visible (libsph_b200 has no CPU path)");
+    }
+    if (p->device < 0 || p->device >= ndev) return sph_fail(nullptr, SPH_ERR_INVALID, "sph_create: bad device ordinal");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess || prop.major != 10)
+        return sph_fail(nullptr, SPH_ERR_NO_DEVICE, "sph_create: device is not sm_100 (kernels are built for sm_100a only)");
+    sph_handle *h = new sph_handle();
+    h->p = *p;
+    h->N = p->N;
+    h->K = p->Kh;
+    const int64_t Q = 1680;  // divisible by every rank count 1..8, 10, 12, 14, 15, 16
+    h->NS = (h->N + Q - 1) / Q * Q;
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            sph_fail(nullptr, SPH_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+            sph_destroy(h);                                                                       \
+            return SPH_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    const size_t N = (size_t)h->N, NS = (size_t)h->NS, K = (size_t)h->K;
+    CK(dalloc(&h->pos, 3 * N)); CK(dalloc(&h->vel, 3 * N)); CK(dalloc(&h->kent, N)); CK(dalloc(&h->acc, 3 * N));
+    CK(dalloc(&h->pos_half, 3 * N)); CK(dalloc(&h->vel_half, 3 * N));
+    CK(dalloc(&h->in_pos, 3 * N)); CK(dalloc(&h->in_vel, 3 * N)); CK(dalloc(&h->in_kent, N)); CK(dalloc(&h->in_acc, 3 * N));
+    CK(dalloc(&h->o_rho, N)); CK(dalloc(&h->o_h, N)); CK(dalloc(&h->o_phi, N)); CK(dalloc(&h->o_sumvdw, N));
+    CK(dalloc(&h->o_mumax, N)); CK(dalloc(&h->o_cs, N)); CK(dalloc(&h->o_dkdt, N)); CK(dalloc(&h->o_ahyd, 3 * N));
+    CK(dalloc(&h->o_g, 3 * N));
+    CK(dalloc(&h->keys, N)); CK(dalloc(&h->keys_alt, N)); CK(dalloc(&h->perm, N)); CK(dalloc(&h->perm_alt, N));
+    CK(dalloc(&h->pos4, NS)); CK(dalloc(&h->vel4, NS)); CK(dalloc(&h->hr, NS)); CK(dalloc(&h->prr, NS));
+    CK(dalloc(&h->cs_s, NS)); CK(dalloc(&h->d2k, NS)); CK(dalloc(&h->nbr, N * K));
+    CK(dalloc(&h->s_ahyd, 3 * NS)); CK(dalloc(&h->s_dkdt, NS)); CK(dalloc(&h->s_sumvdw, NS)); CK(dalloc(&h->s_mumax, NS));
+    CK(dalloc(&h->s_g, 3 * NS)); CK(dalloc(&h->s_phi, NS));
+    CK(dalloc(&h->cnt, N + 1)); CK(dalloc(&h->base, N + 2));
+    CK(cudaMemset(h->hr, 0, NS * sizeof(double2)));
+    CK(cudaMemset(h->s_sumvdw, 0, NS * 8)); CK(cudaMemset(h->s_mumax, 0, NS * 8));
+    CK(cudaMemset(h->s_g, 0, 3 * NS * 8)); CK(cudaMemset(h->s_phi, 0, NS * 8));
+    {
+        SphTree &t = h->tree;
+        double factor = 3.0;
+        if (const char *e = getenv("SPH_B200_NODE_FACTOR")) factor = atof(e) > 1.5 ? atof(e) : 3.0;
+        t.cap = (int64_t)(factor * (double)N) + 1024;
+        const size_t C = (size_t)t.cap;
+        CK(dalloc(&t.nodeI, C)); CK(dalloc(&t.nodeA, C)); CK(dalloc(&t.nodeB, C)); CK(dalloc(&t.nodeC, C));
+        CK(dalloc(&t.nstart, C)); CK(dalloc(&t.ncount, C)); CK(dalloc(&t.ndepth, C));
+        CK(dalloc(&t.old_start, C)); CK(dalloc(&t.old_depth, C));
+        CK(dalloc(&t.dkey_in, C)); CK(dalloc(&t.dkey_out, C)); CK(dalloc(&t.dval_in, C)); CK(dalloc(&t.dval_out, C));
+        CK(dalloc(&t.bfs_of_old, C)); CK(dalloc(&t.level_start, (size_t)SPH_LEVELS + 8));
+        h->sort_tmp_bytes = sph_sort_temp_bytes(t.cap > (int64_t)N + 2 ? t.cap : (int64_t)N + 2);
+        CK(cudaMalloc(&h->sort_tmp, h->sort_tmp_bytes));
+    }
+    CK(dalloc(&h->scal, (size_t)SC_COUNT));
+    CK(cudaMemset(h->scal, 0, sizeof(unsigned long long) * SC_COUNT));
+    CK(cudaMallocHost((void **)&h->h_scal, sizeof(unsigned long long) * SC_COUNT));
+    CK(dalloc(&h->stat_dev, (size_t)32));
+    CK(cudaMemset(h->stat_dev, 0, 32 * sizeof(double)));
+    CK(cudaMallocHost((void **)&h->h_stat, 32 * sizeof(double)));
+    CK(dalloc(&h->red_partial, (size_t)592 * 12));
+    for (int i = 0; i <= PH_COUNT; ++i) CK(cudaEventCreate(&h->ev[i]));
+    CK(cudaDeviceSynchronize());
+#undef CK
+    *out = h;
+    return SPH_OK;
+}
+
+int sph_destroy(sph_handle *h) {
+    if (!h) return SPH_OK;
+    cudaSetDevice(h->p.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->nccl && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t)h->nccl);
+    void *ptrs[] = {h->pos, h->vel, h->kent, h->acc, h->pos_half, h->vel_half, h->in_pos, h->in_vel, h->in_kent,
+                    h->in_acc, h->o_rho, h->o_h, h->o_phi, h->o_sumvdw, h->o_mumax, h->o_cs, h->o_dkdt, h->o_ahyd,
+                    h->o_g, h->keys, h->keys_alt, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->prr,
+                    h->cs_s, h->d2k, h->nbr, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax, h->s_g, h->s_phi, h->cnt,
+                    h->base, h->scal, h->stat_dev, h->red_partial, h->tree.nodeI, h->tree.nodeA, h->tree.nodeB,
+                    h->tree.nodeC, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
+                    h->tree.old_depth, h->tree.dkey_in, h->tree.dkey_out, h->tree.dval_in, h->tree.dval_out,
+                    h->tree.bfs_of_old, h->tree.level_start};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->h_stat) cudaFreeHost(h->h_stat);
+    for (int i = 0; i <= PH_COUNT; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SPH_OK;
+}
+
+int sph_set_stream(sph_handle *h, void *cuda_stream) {
+    if (!h) return SPH_ERR_INVALID;
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (cuda_stream) {
+        if (h->own_stream) cudaStreamDestroy(h->stream);
+        h->stream = (cudaStream_t)cuda_stream;
+        h->own_stream = false;
+    } else if (!h->own_stream) {
+        SPH_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    return SPH_OK;
+}
+
+int sph_synchronize(sph_handle *h) {
+    if (!h) return SPH_ERR_INVALID;
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+int sph_upload(sph_handle *h, const double *pos, const double *vel, const double *K, double t) {
+    if (!h || !pos || !vel) return sph_fail(h, SPH_ERR_INVALID, "sph_upload: null pos/vel");
+    if (h->p.eos == SPH_EOS_POLYTROPIC && !K) return sph_fail(h, SPH_ERR_INVALID, "sph_upload: polytropic EOS needs K");
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    const size_t N = (size_t)h->N;
+    SPH_CUDA(h, cudaMemcpyAsync(h->pos, pos, 3 * N * 8, cudaMemcpyHostToDevice, h->stream));
+    SPH_CUDA(h, cudaMemcpyAsync(h->vel, vel, 3 * N * 8, cudaMemcpyHostToDevice, h->stream));
+    if (K) SPH_CUDA(h, cudaMemcpyAsync(h->kent, K, N * 8, cudaMemcpyHostToDevice, h->stream));
+    SPH_CUDA(h, sph_launch_set_time(h, t));
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->t = t;
+    h->have_state = true;
+    return SPH_OK;
+}
+
+int sph_download(sph_handle *h, double *pos, double *vel, double *K, double *t) {
+    if (!h) return SPH_ERR_INVALID;
+    if (!h->have_state) return sph_fail(h, SPH_ERR_STATE, "sph_download: no state uploaded");
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    const size_t N = (size_t)h->N;
+    if (int rc = d2h(h, pos, h->pos, 3 * N)) return rc;
+    if (int rc = d2h(h, vel, h->vel, 3 * N)) return rc;
+    if (K && h->p.eos == SPH_EOS_POLYTROPIC)
+        if (int rc = d2h(h, K, h->kent, N)) return rc;
+    SPH_CUDA(h, cudaMemcpyAsync(h->h_stat, h->stat_dev, 32 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->t = h->h_stat[0];
+    if (t) *t = h->t;
+    return SPH_OK;
+}
+
+int sph_eval_acc(sph_handle *h, const double *pos, const double *vel, const double *K, double *acc, double *rho,
+                 double *hsml, double *phi) {
+    if (!h || !pos || !vel) return sph_fail(h, SPH_ERR_INVALID, "sph_eval_acc: null pos/vel");
+    const bool poly = h->p.eos == SPH_EOS_POLYTROPIC;
+    if (poly && !K) return sph_fail(h, SPH_ERR_INVALID, "sph_eval_acc: polytropic EOS needs K");
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    const size_t N = (size_t)h->N;
+    SPH_CUDA(h, cudaMemcpyAsync(h->in_pos, pos, 3 * N * 8, cudaMemcpyHostToDevice, h->stream));
+    SPH_CUDA(h, cudaMemcpyAsync(h->in_vel, vel, 3 * N * 8, cudaMemcpyHostToDevice, h->stream));
+    if (poly) SPH_CUDA(h, cudaMemcpyAsync(h->in_kent, K, N * 8, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = eval_internal(h, h->in_pos, h->in_vel, poly ? h->in_kent : nullptr, h->in_acc)) return rc;
+    if (int rc = d2h(h, acc, h->in_acc, 3 * N)) return rc;
+    if (int rc = d2h(h, rho, h->o_rho, N)) return rc;
+    if (int rc = d2h(h, hsml, h->o_h, N)) return rc;
+    if (int rc = d2h(h, phi, h->o_phi, N)) return rc;
+    return check_flags(h);
+}
+
+int sph_eval_state(sph_handle *h) {
+    if (!h) return SPH_ERR_INVALID;
+    if (!h->have_state) return sph_fail(h, SPH_ERR_STATE, "sph_eval_state: no state uploaded");
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    if (int rc = eval_internal(h, h->pos, h->vel, h->p.eos == SPH_EOS_POLYTROPIC ? h->kent : nullptr, h->acc)) return rc;
+    if (int rc = sph_launch_dt(h, h->vel, h->acc) != cudaSuccess ? SPH_ERR_CUDA : 0) return sph_fail(h, rc, "dt launch failed");
+    return check_flags(h);
+}
+
+int sph_step(sph_handle *h, int nsteps, sph_step_info *info) {
+    if (!h || nsteps < 0) return sph_fail(h, SPH_ERR_INVALID, "sph_step: bad argument");
+    if (!h->have_state) return sph_fail(h, SPH_ERR_STATE, "sph_step: no state uploaded");
+    if (nsteps == 0) return SPH_OK;
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    const bool poly = h->p.eos == SPH_EOS_POLYTROPIC;
+    double *log_dev = nullptr;
+    SPH_CUDA(h, cudaMalloc((void **)&log_dev, (size_t)nsteps * 11 * sizeof(double)));
+    int rc = SPH_OK;
+    for (int s = 0; s < nsteps && rc == SPH_OK; ++s) {
+        // getAcc #1, dt, statistics                                   F/isothermal_sim.jl:155-192
+        rc = eval_internal(h, h->pos, h->vel, poly ? h->kent : nullptr, h->acc);
+        if (rc) break;
+        cudaError_t e = sph_launch_dt(h, h->vel, h->acc);
+        if (e == cudaSuccess) e = sph_launch_stats(h, log_dev + (size_t)s * 11);
+        // predictor                                                   :197-200
+        if (e == cudaSuccess) e = sph_launch_predict(h);
+        if (e == cudaSuccess && poly) e = sph_launch_evolve_k(h);      // F/polytrope_sim.jl:217
+        if (e != cudaSuccess) { rc = sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e)); break; }
+        // getAcc #2 at the half step                                  :203
+        rc = eval_internal(h, h->pos_half, h->vel_half, poly ? h->kent : nullptr, h->acc);
+        if (rc) break;
+        if (poly) e = sph_launch_evolve_k(h);                           // F/polytrope_sim.jl:221
+        // corrector, t += dt                                           :206-212
+        if (e == cudaSuccess) e = sph_launch_correct(h);
+        if (e != cudaSuccess) { rc = sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e)); break; }
+    }
+    if (rc == SPH_OK) rc = check_flags(h);
+    if (rc == SPH_OK && info) {
+        double *tmp = (double *)malloc((size_t)nsteps * 11 * sizeof(double));
+        cudaError_t e = cudaMemcpy(tmp, log_dev, (size_t)nsteps * 11 * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e));
+        for (int s = 0; s < nsteps && rc == SPH_OK; ++s) {
+            info[s].dt = tmp[(size_t)s * 11];
+            for (int k = 0; k < 10; ++k) info[s].stats[k] = tmp[(size_t)s * 11 + 1 + k];
+        }
+        free(tmp);
+    }
+    cudaStreamSynchronize(h->stream);
+    cudaFree(log_dev);
+    h->lists_valid = h->lists_valid && rc == SPH_OK;
+    return rc;
+}
+
+int sph_get_neighbors(sph_handle *h, int32_t *idx, double *r) {
+    if (!h) return SPH_ERR_INVALID;
+    if (!h->have_eval || !h->lists_valid) return sph_fail(h, SPH_ERR_STATE, "sph_get_neighbors: no force evaluation yet");
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    const size_t NK = (size_t)h->N * (size_t)h->K;
+    int *d_idx = nullptr;
+    double *d_r = nullptr;
+    if (idx) SPH_CUDA(h, cudaMalloc((void **)&d_idx, NK * 4));
+    if (r) SPH_CUDA(h, cudaMalloc((void **)&d_r, NK * 8));
+    if (h->nranks > 1) {  // rows of other ranks' targets are not held here
+        if (d_idx) cudaMemsetAsync(d_idx, 0, NK * 4, h->stream);
+        if (d_r) cudaMemsetAsync(d_r, 0, NK * 8, h->stream);
+        cudaFree(d_idx); cudaFree(d_r);
+        return sph_fail(h, SPH_ERR_STATE, "sph_get_neighbors: only available on single-GPU handles");
+    }
+    export_nbr_kernel<<<148 * 8, 256, 0, h->stream>>>(h->N, h->K, h->perm, h->nbr, h->pos4, d_idx, d_r);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && idx) e = cudaMemcpyAsync(idx, d_idx, NK * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && r) e = cudaMemcpyAsync(r, d_r, NK * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_idx); cudaFree(d_r);
+    if (e != cudaSuccess) return sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e));
+    return SPH_OK;
+}
+
+int sph_get_hydro(sph_handle *h, double *ahyd, double *rho, double *hsml, double *sum_vdw, double *mumax,
+                  double *cs_i, double *dkdt) {
+    if (!h) return SPH_ERR_INVALID;
+    if (!h->have_eval) return sph_fail(h, SPH_ERR_STATE, "sph_get_hydro: no force evaluation yet");
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    const size_t N = (size_t)h->N;
+    int rc;
+    if ((rc = d2h(h, ahyd, h->o_ahyd, 3 * N)) || (rc = d2h(h, rho, h->o_rho, N)) || (rc = d2h(h, hsml, h->o_h, N)) ||
+        (rc = d2h(h, sum_vdw, h->o_sumvdw, N)) || (rc = d2h(h, mumax, h->o_mumax, N)) ||
+        (rc = d2h(h, cs_i, h->o_cs, N)) || (rc = d2h(h, dkdt, h->o_dkdt, N)))
+        return rc;
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+int sph_get_grav(sph_handle *h, double *g, double *phi) {
+    if (!h) return SPH_ERR_INVALID;
+    if (!h->have_eval) return sph_fail(h, SPH_ERR_STATE, "sph_get_grav: no force evaluation yet");
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    int rc;
+    if ((rc = d2h(h, g, h->o_g, 3 * (size_t)h->N)) || (rc = d2h(h, phi, h->o_phi, (size_t)h->N))) return rc;
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+int sph_get_acc(sph_handle *h, double *acc) {
+    if (!h) return SPH_ERR_INVALID;
+    if (!h->have_eval) return sph_fail(h, SPH_ERR_STATE, "sph_get_acc: no force evaluation yet");
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    if (int rc = d2h(h, acc, h->last_acc, 3 * (size_t)h->N)) return rc;
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+int sph_get_octree(sph_handle *h, double *nodes, int64_t cap, int64_t *n_nodes) {
+    if (!h) return SPH_ERR_INVALID;
+    if (!h->have_eval) return sph_fail(h, SPH_ERR_STATE, "sph_get_octree: no force evaluation yet");
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    SPH_CUDA(h, cudaMemcpyAsync(h->h_scal, h->scal, sizeof(unsigned long long) * SC_COUNT, cudaMemcpyDeviceToHost, h->stream));
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int64_t M = (int64_t)h->h_scal[SC_NNODES];
+    if (n_nodes) *n_nodes = M;
+    if (!nodes) return SPH_OK;
+    const int64_t n = M < cap ? M : cap;
+    if (n <= 0) return SPH_OK;
+    double *d = nullptr;
+    SPH_CUDA(h, cudaMalloc((void **)&d, (size_t)n * 16 * 8));
+    export_tree_kernel<<<148 * 4, 256, 0, h->stream>>>(h->tree, h->scal, h->p.m, n, d);
+    export_tree_centres_kernel<<<148 * 4, 256, 0, h->stream>>>(h->tree, h->scal, h->keys, n, d);
+    cudaError_t e = cudaMemcpyAsync(nodes, d, (size_t)n * 16 * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e));
+    return SPH_OK;
+}
+
+int sph_get_timings(sph_handle *h, sph_timings *out) {
+    if (!h || !out) return SPH_ERR_INVALID;
+    if (!h->ev_valid) return sph_fail(h, SPH_ERR_STATE, "sph_get_timings: no force evaluation yet");
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    SPH_CUDA(h, cudaEventSynchronize(h->ev[PH_COUNT]));
+    float ms[PH_COUNT];
+    for (int i = 0; i < PH_COUNT; ++i) SPH_CUDA(h, cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+    out->sort_ms = ms[PH_SORT]; out->tree_ms = ms[PH_TREE]; out->knn_ms = ms[PH_KNN];
+    out->density_ms = ms[PH_DENSITY]; out->force_ms = ms[PH_FORCE]; out->gravity_ms = ms[PH_GRAV];
+    out->finish_ms = ms[PH_FINISH];
+    float tot;
+    SPH_CUDA(h, cudaEventElapsedTime(&tot, h->ev[0], h->ev[PH_COUNT]));
+    out->total_ms = tot;
+    SPH_CUDA(h, cudaMemcpy(h->h_scal, h->scal, sizeof(unsigned long long) * SC_COUNT, cudaMemcpyDeviceToHost));
+    out->walk_visits = (double)h->h_scal[SC_VISITS];
+    return SPH_OK;
+}
+
+int sph_get_dt(sph_handle *h, double *dt) {
+    if (!h || !dt) return SPH_ERR_INVALID;
+    if (!h->have_eval) return sph_fail(h, SPH_ERR_STATE, "sph_get_dt: no force evaluation yet");
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    SPH_CUDA(h, cudaMemcpyAsync(h->h_stat, h->stat_dev, 32 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    *dt = h->h_stat[1];
+    return SPH_OK;
+}
+
+int sph_density_at(sph_handle *h, const double *pts, int64_t M, double *rho_out) {
+    if (!h || !pts || !rho_out || M < 0) return sph_fail(h, SPH_ERR_INVALID, "sph_density_at: bad argument");
+    if (!h->have_state) return sph_fail(h, SPH_ERR_STATE, "sph_density_at: no state uploaded");
+    if (M == 0) return SPH_OK;
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    // search structure of the uploaded positions (keys, sort, tree); neighbour lists of an earlier
+    // evaluation no longer match it afterwards
+    h->lists_valid = false;
+    SPH_CUDA(h, sph_launch_domain_keys(h, h->pos));
+    SPH_CUDA(h, sph_launch_permute(h, h->pos, h->vel, nullptr));
+    SPH_CUDA(h, sph_launch_tree(h));
+    double *d_pts = nullptr, *d_rho = nullptr;
+    SPH_CUDA(h, cudaMalloc((void **)&d_pts, (size_t)M * 3 * 8));
+    SPH_CUDA(h, cudaMalloc((void **)&d_rho, (size_t)M * 8));
+    cudaError_t e = cudaMemcpyAsync(d_pts, pts, (size_t)M * 3 * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = sph_launch_knn_points(h, d_pts, M, d_rho);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rho_out, d_rho, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream);
+    sticky_kernel<<<1, 1, 0, h->stream>>>(h->scal);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_pts); cudaFree(d_rho);
+    if (e != cudaSuccess) return sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e));
+    return check_flags(h);
+}
+
+int sph_comm_unique_id(void *id128) {
+    if (!id128) return SPH_ERR_INVALID;
+    NcclApi &nc = nccl_api();
+    if (!nc.ok) return sph_fail(nullptr, SPH_ERR_NCCL, nc.why);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = nc.GetUniqueId(&id);
+    if (r != ncclSuccess) return sph_fail(nullptr, SPH_ERR_NCCL, nc.GetErrorString(r));
+    memcpy(id128, &id, 128);
+    return SPH_OK;
+}
+
+int sph_comm_init(sph_handle *h, int nranks, int rank, const void *id128) {
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return sph_fail(h, SPH_ERR_INVALID, "sph_comm_init: bad argument");
+    if (h->NS % nranks != 0) return sph_fail(h, SPH_ERR_INVALID, "sph_comm_init: unsupported rank count (use 1-8, 10, 12, 14, 15 or 16)");
+    if (nranks == 1) { h->nranks = 1; h->rank = 0; return SPH_OK; }
+    NcclApi &nc = nccl_api();
+    if (!nc.ok) return sph_fail(h, SPH_ERR_NCCL, nc.why);
+    SPH_CUDA(h, cudaSetDevice(h->p.device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    SPH_NCCL(h, nc.CommInitRank(&comm, nranks, id, rank));
+    h->nccl = comm;
+    h->nranks = nranks;
+    h->rank = rank;
+    return SPH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+// sph_internal.cuh -- shared declarations of libsph_b200.so (not part of the public ABI).
+//
+// Device data layout (per handle, all FP64 unless noted; "sorted" = octant-key order of the
+// CURRENT evaluation, "orig" = the caller's particle order):
+//   state   pos[3N] vel[3N] kent[N] acc[3N]                      orig, column-major like the Julia matrices
+//   sort    keys[N] u64 (21 levels x 3 bits), perm[N] i32        perm[s] = orig id of sorted slot s
+//   sorted  pos4[N] double4 {x,y,z,h}, vel4[N] double4 {vx,vy,vz,K_i}, hr[N] double2 {h,rho}
+//   tree    BFS-ordered linear octree: nodeI int2 {first child | particle, nchild (0 = leaf)},
+//           nodeA double4 {com, mass}, nodeB double4 {lo.xyz, hi.x}, nodeC double4 {hi.y, hi.z, (2L)^2, L},
+//           nstart/ncount i32 particle range of the node in the sorted arrays
+//   lists   nbr[N x K] i32 column-major, sorted-space rows and entries (0-based), d2k[N]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/sph_b200.h"
+
+#define SPH_LEVELS 21           // octant levels held by one 63-bit key
+#define SPH_MAX_RANKS 16
+
+#define HD __host__ __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------------------
+// Octant path key.  Replays the child-centre recurrence of addNodes! (F/gravOctree_Single.jl:110-126,
+// :143-148): child_l = parent_l/2, child centre = parent centre -/+ child_l, octant bit = (x - c) > 0.
+// Only additions, subtractions and halvings: bit-identical to the Julia evaluation, so a particle
+// on a cell boundary lands in the same child as in the reference.
+// ---------------------------------------------------------------------------------------------
+HD uint64_t sph_octant_key(double x, double y, double z, double l) {
+    double cx = 0.0, cy = 0.0, cz = 0.0, L = l;
+    uint64_t key = 0;
+#pragma unroll 1
+    for (int lev = 0; lev < SPH_LEVELS; ++lev) {
+        const double cl = L / 2;
+        const unsigned ox = (x - cx) > 0, oy = (y - cy) > 0, oz = (z - cz) > 0;
+        key = (key << 3) | (uint64_t)((oz << 2) | (oy << 1) | ox);
+        cx = ox ? cx + cl : cx - cl;
+        cy = oy ? cy + cl : cy - cl;
+        cz = oz ? cz + cl : cz - cl;
+        L = cl;
+    }
+    return key;
+}
+
+// Geometry of the depth-d cell on the path `key`: centre, bounds and half-width exactly as
+// addNodes! produces them (F/gravOctree_Single.jl:110-140): for a parent (pc, pl): cl = pl/2,
+// lc = pc-cl, rc = pc+cl, mn = lc-cl, ctr = lc+cl, mx = rc+cl; low child = {lc,[mn,ctr]}, high = {rc,[ctr,mx]}.
+struct SphCell {
+    double c[3], lo[3], hi[3], L;
+};
+HD SphCell sph_cell_of(uint64_t key, int depth, double l) {
+    SphCell g;
+    g.L = l;
+    for (int a = 0; a < 3; ++a) { g.c[a] = 0.0; g.lo[a] = -l; g.hi[a] = l; }
+#pragma unroll 1
+    for (int lev = 0; lev < depth; ++lev) {
+        const double cl = g.L / 2;
+        const unsigned oct = (unsigned)(key >> (3 * (SPH_LEVELS - 1 - lev))) & 7u;
+        for (int a = 0; a < 3; ++a) {
+            const double lc = g.c[a] - cl, rc = g.c[a] + cl;
+            const double mn = lc - cl, ctr = lc + cl, mx = rc + cl;
+            if ((oct >> a) & 1u) { g.c[a] = rc; g.lo[a] = ctr; g.hi[a] = mx; }
+            else                 { g.c[a] = lc; g.lo[a] = mn;  g.hi[a] = ctr; }
+        }
+        g.L = cl;
+    }
+    return g;
+}
+
+// number of leading octant levels two keys share (21 = identical keys)
+HD int sph_common_levels(uint64_t a, uint64_t b) {
+    const uint64_t x = a ^ b;
+    if (x == 0) return SPH_LEVELS;
+#ifdef __CUDA_ARCH__
+    const int lz = __clzll((long long)x);
+#else
+    const int lz = __builtin_clzll(x);
+#endif
+    return (lz - 1) / 3;
+}
+
+#ifdef __CUDACC__
+// Squared distance exactly as NearestNeighbors' Euclidean metric evaluates it in the oracle's
+// restatement: (dx*dx + dy*dy) + dz*dz with every product and sum rounded (never contracted to FMA).
+__device__ __forceinline__ double sph_d2_exact(double dx, double dy, double dz) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+enum { PH_SORT = 0, PH_TREE, PH_KNN, PH_DENSITY, PH_FORCE, PH_GRAV, PH_FINISH, PH_COUNT };
+
+struct SphTree {
+    int64_t cap = 0;  // node capacity
+    int2 *nodeI = nullptr;
+    double4 *nodeA = nullptr, *nodeB = nullptr, *nodeC = nullptr;
+    int *nstart = nullptr, *ncount = nullptr, *ndepth = nullptr;
+    // build scratch
+    int *old_start = nullptr, *old_depth = nullptr;  // node list in (start, depth) order
+    uint64_t *dkey_in = nullptr, *dkey_out = nullptr;
+    int *dval_in = nullptr, *dval_out = nullptr;      // bfs -> old
+    int *bfs_of_old = nullptr;
+    int *level_start = nullptr;                       // [SPH_LEVELS + 3]
+};
+
+struct sph_handle {
+    sph_params p{};
+    int64_t N = 0;
+    int64_t NS = 0;  // stride of the sorted-space component arrays: N rounded up so every rank count divides it
+    int K = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    bool have_state = false, have_eval = false;
+    double t = 0.0;
+
+    // state (orig order)
+    double *pos = nullptr, *vel = nullptr, *kent = nullptr, *acc = nullptr;
+    double *pos_half = nullptr, *vel_half = nullptr;
+    // staging for sph_eval_acc
+    double *in_pos = nullptr, *in_vel = nullptr, *in_kent = nullptr, *in_acc = nullptr;
+    const double *last_acc = nullptr;  // acceleration array written by the last evaluation
+    bool lists_valid = false;          // neighbour lists match the current sort
+    // per-evaluation outputs, orig order
+    double *o_rho = nullptr, *o_h = nullptr, *o_phi = nullptr, *o_sumvdw = nullptr, *o_mumax = nullptr,
+           *o_cs = nullptr, *o_dkdt = nullptr, *o_ahyd = nullptr, *o_g = nullptr;
+    // sort
+    uint64_t *keys = nullptr, *keys_alt = nullptr;
+    int *perm = nullptr, *perm_alt = nullptr;
+    void *sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    // sorted working set
+    double4 *pos4 = nullptr, *vel4 = nullptr;
+    double2 *hr = nullptr;
+    double *prr = nullptr;      // P/rho^2 (sorted)
+    double *cs_s = nullptr;     // sound speed (sorted)
+    double *d2k = nullptr;
+    int *nbr = nullptr;         // N x K
+    double *s_ahyd = nullptr;   // 3N, sorted: direct + scattered hydro acceleration
+    double *s_dkdt = nullptr, *s_sumvdw = nullptr, *s_mumax = nullptr;
+    double *s_g = nullptr;      // 3N sorted
+    double *s_phi = nullptr;
+    int *cnt = nullptr, *base = nullptr;  // per-particle node counts / offsets (N+1)
+    SphTree tree;
+    // device scalars: [0] l_domain bits, [1] n_nodes, [2] error flags, [3] dt bits, [4] visits
+    unsigned long long *scal = nullptr;
+    unsigned long long *h_scal = nullptr;  // pinned mirror
+    double *stat_dev = nullptr;            // 32 doubles: t, dt, reduction results, stats row (integrate.cu)
+    double *h_stat = nullptr;              // pinned mirror
+    double *red_partial = nullptr;         // per-block partial sums of the statistics kernels
+    // timing
+    cudaEvent_t ev[PH_COUNT + 1]{};
+    bool ev_valid = false;
+    // multi-GPU
+    int nranks = 1, rank = 0;
+    void *nccl = nullptr;
+    int64_t chunk = 0;  // targets per rank (padded)
+};
+
+// scal[0..SC_RESET) is cleared at the start of every force evaluation; SC_STICKY accumulates error flags
+enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_RESET = 6, SC_STICKY = 6, SC_COUNT = 8 };
+enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4 };
+
+int sph_fail(sph_handle *h, int code, const std::string &msg);
+#define SPH_CUDA(h, call)                                                                            \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return sph_fail((h), SPH_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---- radix_sort.cu ------------------------------------------------------------------------------
+size_t sph_sort_temp_bytes(int64_t n);
+// Stable LSD radix sort of (key, value) pairs on bits [begin_bit, end_bit).  Result lands in
+// keys_out/vals_out (ping-pongs through the *_in buffers, which are clobbered).
+cudaError_t sph_sort_pairs(uint64_t *keys_in, int *vals_in, uint64_t *keys_out, int *vals_out, int64_t n,
+                           const unsigned long long *n_dev /* optional device-side n (<= n) */,
+                           int begin_bit, int end_bit, void *temp, size_t temp_bytes, cudaStream_t st);
+// exclusive scan of n ints; out[n] = total (out has n+1 entries)
+cudaError_t sph_exclusive_scan(const int *in, int *out, int64_t n, void *temp, size_t temp_bytes,
+                               cudaStream_t st);
+
+// ---- tree.cu -------------------------------------------------------------------------------------
+cudaError_t sph_launch_domain_keys(sph_handle *h, const double *pos);
+cudaError_t sph_launch_permute(sph_handle *h, const double *pos, const double *vel, const double *kent);
+cudaError_t sph_launch_tree(sph_handle *h);
+
+// ---- knn.cu --------------------------------------------------------------------------------------
+cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1);
+cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t M, double *rho_out_dev);
+
+// ---- hydro.cu ------------------------------------------------------------------------------------
+cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1);
+cudaError_t sph_launch_eos(sph_handle *h);
+cudaError_t sph_launch_force(sph_handle *h, int64_t t0, int64_t t1);
+
+// ---- gravity.cu ----------------------------------------------------------------------------------
+cudaError_t sph_launch_walk(sph_handle *h, int64_t t0, int64_t t1);
+
+// ---- integrate.cu --------------------------------------------------------------------------------
+cudaError_t sph_launch_finish(sph_handle *h, double *acc_out);
+cudaError_t sph_launch_dt(sph_handle *h, const double *vel, const double *acc);
+cudaError_t sph_launch_stats(sph_handle *h, double *log_row_dev);
+cudaError_t sph_launch_set_time(sph_handle *h, double t);
+cudaError_t sph_launch_predict(sph_handle *h);
+cudaError_t sph_launch_correct(sph_handle *h);
+cudaError_t sph_launch_evolve_k(sph_handle *h);
