@@ -40,7 +40,7 @@ __device__ __forceinline__ void grav_kernels(double r, double h, double &gPHI, d
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(GW_WARPS * 32) walk_kernel(int64_t N, int64_t t0, int64_t t1,
+__global__ void __launch_bounds__(GW_WARPS * 32) walk_kernel(int64_t NS, int64_t t0, int64_t t1,
                                                               const double4 *__restrict__ pos4, SphTree t,
                                                               double theta_sq, double m,
                                                               unsigned long long *__restrict__ scal,
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32) walk_kernel(int64_t N, int64_t 
         __syncwarp();
     }
     if (active) {
-        g[s] = gx; g[s + N] = gy; g[s + 2 * N] = gz;
+        g[s] = gx; g[s + NS] = gy; g[s + 2 * NS] = gz;
         phi[s] = ph - (m * (7.0 / 5) / hi);                                      // (:303)
     }
     if (COUNT) {
@@ -152,10 +152,10 @@ cudaError_t sph_launch_walk(sph_handle *h, int64_t t0, int64_t t1) {
     const double th2 = h->p.theta * h->p.theta;
     static const bool count = getenv("SPH_B200_COUNT_VISITS") != nullptr;
     if (count)
-        walk_kernel<true><<<(int)blocks, GW_WARPS * 32, 0, h->stream>>>(h->N, t0, t1, h->pos4, h->tree, th2, h->p.m,
+        walk_kernel<true><<<(int)blocks, GW_WARPS * 32, 0, h->stream>>>(h->NS, t0, t1, h->pos4, h->tree, th2, h->p.m,
                                                                         h->scal, h->s_g, h->s_phi);
     else
-        walk_kernel<false><<<(int)blocks, GW_WARPS * 32, 0, h->stream>>>(h->N, t0, t1, h->pos4, h->tree, th2, h->p.m,
+        walk_kernel<false><<<(int)blocks, GW_WARPS * 32, 0, h->stream>>>(h->NS, t0, t1, h->pos4, h->tree, th2, h->p.m,
                                                                          h->scal, h->s_g, h->s_phi);
     return cudaGetLastError();
 }

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(HB) eos_kernel(int64_t N, const double2 *__res
 
 // Pair loop of hydroCalculation / getAV / evolve_K!.  The target's own update is kept in registers and
 // stored once; the reaction on the neighbour (a_j += ct*gradW, dK_j += c2) is a double-precision RED to L2.
-__global__ void __launch_bounds__(HB) force_kernel(int64_t N, int K, int64_t t0, int64_t t1,
+__global__ void __launch_bounds__(HB) force_kernel(int64_t N, int64_t NS, int K, int64_t t0, int64_t t1,
                                                     const double4 *__restrict__ pos4, const double4 *__restrict__ vel4,
                                                     const double2 *__restrict__ hr, const double *__restrict__ prr,
                                                     const double *__restrict__ cs_s, const int *__restrict__ nbr,
@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(HB) force_kernel(int64_t N, int K, int64_t t0,
         const double fx = ct * gx, fy = ct * gy, fz = ct * gz;
         ax -= fx; ay -= fy; az -= fz;
         atomicAdd(&ahyd[nj], fx);
-        atomicAdd(&ahyd[nj + N], fy);
-        atomicAdd(&ahyd[nj + 2 * N], fz);
+        atomicAdd(&ahyd[nj + NS], fy);
+        atomicAdd(&ahyd[nj + 2 * NS], fz);
         if (poly) {
             const double c2 = m * Pi * vdw / 2;                              // evolve_K! poly :305-311
             dk += c2;
@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(HB) force_kernel(int64_t N, int K, int64_t t0,
         }
     }
     atomicAdd(&ahyd[s], ax);
-    atomicAdd(&ahyd[s + N], ay);
-    atomicAdd(&ahyd[s + 2 * N], az);
+    atomicAdd(&ahyd[s + NS], ay);
+    atomicAdd(&ahyd[s + 2 * NS], az);
     if (poly) atomicAdd(&dkdt[s], dk);
     sumvdw[s] = svdw;
     mumax[s] = mmax;
@@ -167,12 +167,12 @@ cudaError_t sph_launch_eos(sph_handle *h) {
 
 cudaError_t sph_launch_force(sph_handle *h, int64_t t0, int64_t t1) {
     const int64_t N = h->N;
-    cudaMemsetAsync(h->s_ahyd, 0, sizeof(double) * 3 * N, h->stream);
-    cudaMemsetAsync(h->s_dkdt, 0, sizeof(double) * N, h->stream);
+    cudaMemsetAsync(h->s_ahyd, 0, sizeof(double) * 3 * h->NS, h->stream);
+    cudaMemsetAsync(h->s_dkdt, 0, sizeof(double) * h->NS, h->stream);
     if (t1 <= t0) return cudaGetLastError();
     const int64_t nt = t1 - t0;
     force_kernel<<<(int)((nt + HB - 1) / HB), HB, 0, h->stream>>>(
-        N, h->K, t0, t1, h->pos4, h->vel4, h->hr, h->prr, h->cs_s, h->nbr, h->p.m, h->p.alpha, h->p.beta,
+        N, h->NS, h->K, t0, t1, h->pos4, h->vel4, h->hr, h->prr, h->cs_s, h->nbr, h->p.m, h->p.alpha, h->p.beta,
         h->p.eos == SPH_EOS_POLYTROPIC, h->scal, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax);
     return cudaGetLastError();
 }

@@ -30,7 +30,9 @@
 HD uint64_t sph_octant_key(double x, double y, double z, double l) {
     double cx = 0.0, cy = 0.0, cz = 0.0, L = l;
     uint64_t key = 0;
+#ifdef __CUDA_ARCH__
 #pragma unroll 1
+#endif
     for (int lev = 0; lev < SPH_LEVELS; ++lev) {
         const double cl = L / 2;
         const unsigned ox = (x - cx) > 0, oy = (y - cy) > 0, oz = (z - cz) > 0;
@@ -53,7 +55,9 @@ HD SphCell sph_cell_of(uint64_t key, int depth, double l) {
     SphCell g;
     g.L = l;
     for (int a = 0; a < 3; ++a) { g.c[a] = 0.0; g.lo[a] = -l; g.hi[a] = l; }
+#ifdef __CUDA_ARCH__
 #pragma unroll 1
+#endif
     for (int lev = 0; lev < depth; ++lev) {
         const double cl = g.L / 2;
         const unsigned oct = (unsigned)(key >> (3 * (SPH_LEVELS - 1 - lev))) & 7u;

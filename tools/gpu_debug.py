@@ -111,7 +111,7 @@ def run_case(eos, ic_type, N, nthreads, dump=True, steps=0, **kw):
             print(f"oracle {steps} steps {time.time() - t0:.2f}s dts {oo['dts']}")
             print("dt relerr", relerr(info["dts"], oo["dts"]), " t", gt, oo["t"])
             print("pos relerr(vec)", vec_relerr(gp, oo["pos"]), " vel vec relerr", vec_relerr(gv, oo["vel"]))
-            print("stats relerr per column", [relerr(info["stats"][:, k], oo["stats"][:, k], 1e-300) for k in range(10)])
+            print("stats |diff| per column", [float(np.abs(info["stats"][:, k] - oo["stats"][:, k]).max()) for k in range(10)])
             print("stats gpu row0", info["stats"][0]); print("stats ora row0", oo["stats"][0])
             if gK is not None:
                 print("K relerr", relerr(gK, oo["K"]))
