@@ -145,8 +145,10 @@ __global__ void leaf_h_kernel(SphTree t, const double4 *__restrict__ pos4, const
 }  // namespace
 
 cudaError_t sph_launch_walk(sph_handle *h, int64_t t0, int64_t t1) {
+    sph_note(1);
     leaf_h_kernel<<<148 * 8, 256, 0, h->stream>>>(h->tree, h->pos4, h->scal);
     if (t1 <= t0) return cudaGetLastError();
+    sph_note(1);
     const int64_t nt = t1 - t0;
     const int64_t blocks = (nt + GW_WARPS * 32 - 1) / (GW_WARPS * 32);
     const double th2 = h->p.theta * h->p.theta;

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(HB) force_kernel(int64_t N, int64_t NS, int K,
 
 cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1) {
     if (t1 <= t0) return cudaSuccess;
+    sph_note(1);
     const int64_t nt = t1 - t0;
     density_kernel<<<(int)((nt + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->K, t0, t1, h->pos4, h->nbr, h->d2k,
                                                                     h->p.m, h->p.eos == SPH_EOS_POLYTROPIC, h->scal,
@@ -159,6 +160,7 @@ cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1) {
 }
 
 cudaError_t sph_launch_eos(sph_handle *h) {
+    sph_note(1);
     eos_kernel<<<(int)((h->N + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->hr, h->vel4,
                                                                   h->p.eos == SPH_EOS_POLYTROPIC, h->p.cs, h->p.gamma,
                                                                   h->scal, h->prr, h->cs_s, h->pos4);
@@ -170,6 +172,7 @@ cudaError_t sph_launch_force(sph_handle *h, int64_t t0, int64_t t1) {
     cudaMemsetAsync(h->s_ahyd, 0, sizeof(double) * 3 * h->NS, h->stream);
     cudaMemsetAsync(h->s_dkdt, 0, sizeof(double) * h->NS, h->stream);
     if (t1 <= t0) return cudaGetLastError();
+    sph_note(1);
     const int64_t nt = t1 - t0;
     force_kernel<<<(int)((nt + HB - 1) / HB), HB, 0, h->stream>>>(
         N, h->NS, h->K, t0, t1, h->pos4, h->vel4, h->hr, h->prr, h->cs_s, h->nbr, h->p.m, h->p.alpha, h->p.beta,

@@ -217,6 +217,7 @@ __global__ void set_time_kernel(double *dv, double t) { dv[DV_T] = t; }
 }  // namespace
 
 cudaError_t sph_launch_finish(sph_handle *h, double *acc_out) {
+    sph_note(1);
     finish_kernel<<<grid_for(h->N), IB, 0, h->stream>>>(h->N, h->NS, h->perm, h->s_ahyd, h->s_g, h->hr, h->s_phi,
                                                          h->s_sumvdw, h->s_mumax, h->cs_s, h->s_dkdt, h->p.G, acc_out,
                                                          h->o_ahyd, h->o_g, h->o_rho, h->o_h, h->o_phi, h->o_sumvdw,
@@ -225,6 +226,7 @@ cudaError_t sph_launch_finish(sph_handle *h, double *acc_out) {
 }
 
 cudaError_t sph_launch_dt(sph_handle *h, const double *vel, const double *acc) {
+    sph_note(3);
     dt_init_kernel<<<1, 1, 0, h->stream>>>(h->scal);
     dt_kernel<<<RED_BLOCKS, IB, 0, h->stream>>>(h->N, vel, acc, h->o_rho, h->o_h, h->o_sumvdw, h->o_mumax, h->o_cs,
                                                  h->p.m, h->p.alpha, h->p.beta, h->scal);
@@ -234,6 +236,7 @@ cudaError_t sph_launch_dt(sph_handle *h, const double *vel, const double *acc) {
 
 cudaError_t sph_launch_stats(sph_handle *h, double *log_row) {
     const bool poly = h->p.eos == SPH_EOS_POLYTROPIC;
+    sph_note(5);
     stats1_kernel<<<RED_BLOCKS, IB, 0, h->stream>>>(h->N, h->pos, h->vel, h->o_phi, h->o_rho, poly ? h->kent : nullptr,
                                                      h->p.gamma, h->red_partial);
     final_sum_kernel<9><<<1, IB, 0, h->stream>>>(h->red_partial, RED_BLOCKS, h->stat_dev + DV_SUM);
@@ -244,23 +247,27 @@ cudaError_t sph_launch_stats(sph_handle *h, double *log_row) {
 }
 
 cudaError_t sph_launch_predict(sph_handle *h) {
+    sph_note(1);
     predict_kernel<<<grid_for(3 * h->N), IB, 0, h->stream>>>(3 * h->N, h->pos, h->vel, h->acc, h->stat_dev,
                                                               h->pos_half, h->vel_half);
     return cudaGetLastError();
 }
 
 cudaError_t sph_launch_correct(sph_handle *h) {
+    sph_note(2);
     correct_kernel<<<grid_for(3 * h->N), IB, 0, h->stream>>>(3 * h->N, h->pos, h->vel, h->acc, h->stat_dev);
     advance_time_kernel<<<1, 1, 0, h->stream>>>(h->stat_dev);
     return cudaGetLastError();
 }
 
 cudaError_t sph_launch_evolve_k(sph_handle *h) {
+    sph_note(1);
     evolve_k_kernel<<<grid_for(h->N), IB, 0, h->stream>>>(h->N, h->kent, h->o_rho, h->o_dkdt, h->p.gamma, h->stat_dev);
     return cudaGetLastError();
 }
 
 cudaError_t sph_launch_set_time(sph_handle *h, double t) {
+    sph_note(1);
     set_time_kernel<<<1, 1, 0, h->stream>>>(h->stat_dev, t);
     return cudaGetLastError();
 }

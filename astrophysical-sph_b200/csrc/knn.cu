@@ -200,6 +200,7 @@ __global__ void point_density_kernel(int64_t M, int K, const double *__restrict_
 
 cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1) {
     if (t1 <= t0) return cudaSuccess;
+    sph_note(1);
     const int64_t nt = t1 - t0;
     int64_t blocks = (nt + KNN_WARPS - 1) / KNN_WARPS;
     const int64_t cap = 148 * 8 * 4;
@@ -216,6 +217,7 @@ cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1) {
 // pts_dev: M x 3 column-major device points; scratch d2 (M x K) is carved from h->s_g / caller
 cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t M, double *rho_out_dev) {
     if (M <= 0) return cudaSuccess;
+    sph_note(2);
     double *d2s = nullptr;
     cudaError_t e = cudaMallocAsync((void **)&d2s, (size_t)M * h->K * sizeof(double), h->stream);
     if (e != cudaSuccess) return e;

@@ -205,6 +205,7 @@ cudaError_t sph_exclusive_scan(const int *in, int *out, int64_t n, void *temp, s
     const int ntiles = (int)cdiv(n, SC_TILE);
     if ((size_t)(ntiles + 2) * 4 > temp_bytes) return cudaErrorInvalidValue;
     int *tile_sum = (int *)temp;
+    sph_note(3);
     scan_tile_sums<<<ntiles, SC_THREADS, 0, st>>>(in, n, tile_sum);
     scan_of_sums<<<1, 1024, 0, st>>>(tile_sum, ntiles);
     scan_apply<<<ntiles, SC_THREADS, 0, st>>>(in, out, n, tile_sum, ntiles);
@@ -232,6 +233,7 @@ cudaError_t sph_sort_pairs(uint64_t *keys_in, int *vals_in, uint64_t *keys_out, 
     int *va = vals_in, *vb = vals_out;
     for (int p = 0; p < npass; ++p) {
         const int shift = begin_bit + p * RS_BITS;
+        sph_note(2);
         rs_hist_kernel<<<ntiles, RS_THREADS, 0, st>>>(ka, n, n_dev, shift, ghist, ntiles);
         cudaError_t e = sph_exclusive_scan(ghist, goff, hist, scan_tmp, scan_tmp_bytes, st);
         if (e != cudaSuccess) return e;

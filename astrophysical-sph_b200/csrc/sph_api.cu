@@ -179,6 +179,7 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     }
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_GRAV + 1], st));
     SPH_CUDA(h, sph_launch_finish(h, acc_out));
+    sph_note(1);
     sticky_kernel<<<1, 1, 0, st>>>(h->scal);
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_FINISH + 1], st));
     h->ev_valid = true;
@@ -196,6 +197,8 @@ int d2h(sph_handle *h, double *dst, const double *src, size_t n) {
 
 }  // namespace
 
+long long g_sph_launches = 0;
+
 int sph_fail(sph_handle *h, int code, const std::string &msg) {
     if (h) h->err = msg; else g_create_err = msg;
     return code;
@@ -204,6 +207,8 @@ int sph_fail(sph_handle *h, int code, const std::string &msg) {
 extern "C" {
 
 int sph_abi_version(void) { return SPH_B200_ABI_VERSION; }
+
+int64_t sph_launch_count(void) { return (int64_t)g_sph_launches; }
 
 int sph_device_count(void) {
     int n = 0;

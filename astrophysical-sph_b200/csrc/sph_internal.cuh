@@ -169,6 +169,9 @@ enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_RESET = 6, SC_STICKY
 enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4 };
 
 int sph_fail(sph_handle *h, int code, const std::string &msg);
+// cumulative count of kernel launches issued by the library in this process (bench.py's gpu_launches)
+extern long long g_sph_launches;
+inline void sph_note(int n) { g_sph_launches += n; }
 #define SPH_CUDA(h, call)                                                                            \
     do {                                                                                             \
         cudaError_t e__ = (call);                                                                    \

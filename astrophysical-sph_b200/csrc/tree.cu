@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(TB) com_level_kernel(int level, const int *__r
 cudaError_t sph_launch_domain_keys(sph_handle *h, const double *pos) {
     cudaStream_t st = h->stream;
     cudaMemsetAsync(h->scal, 0, sizeof(unsigned long long) * SC_RESET, st);
+    sph_note(2);
     absmax_kernel<<<grid_for(3 * h->N), TB, 0, st>>>(pos, 3 * h->N, h->scal);
     keys_kernel<<<grid_for(h->N), TB, 0, st>>>(pos, h->N, h->scal, h->keys_alt, h->perm_alt);
     return sph_sort_pairs(h->keys_alt, h->perm_alt, h->keys, h->perm, h->N, nullptr, 0, 64, h->sort_tmp,
@@ -209,6 +210,7 @@ cudaError_t sph_launch_domain_keys(sph_handle *h, const double *pos) {
 }
 
 cudaError_t sph_launch_permute(sph_handle *h, const double *pos, const double *vel, const double *kent) {
+    sph_note(1);
     permute_kernel<<<grid_for(h->N), TB, 0, h->stream>>>(pos, vel, kent, h->perm, h->N, h->pos4, h->vel4);
     return cudaGetLastError();
 }
@@ -217,6 +219,7 @@ cudaError_t sph_launch_tree(sph_handle *h) {
     cudaStream_t st = h->stream;
     SphTree &t = h->tree;
     const int64_t N = h->N;
+    sph_note(5 + SPH_LEVELS);
     node_count_kernel<<<grid_for(N), TB, 0, st>>>(h->keys, N, h->cnt, h->scal);
     cudaError_t e = sph_exclusive_scan(h->cnt, h->base, N, h->sort_tmp, h->sort_tmp_bytes, st);
     if (e != cudaSuccess) return e;

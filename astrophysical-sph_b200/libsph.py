@@ -28,7 +28,7 @@ SPH_ERR_TREE_NODES, SPH_ERR_NCCL, SPH_ERR_STATE = -5, -6, -7
 
 # every symbol include/sph_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = (
-    "sph_create", "sph_destroy", "sph_last_error", "sph_abi_version", "sph_device_count", "sph_set_stream",
+    "sph_create", "sph_destroy", "sph_last_error", "sph_abi_version", "sph_launch_count", "sph_device_count", "sph_set_stream",
     "sph_synchronize", "sph_upload", "sph_download", "sph_eval_acc", "sph_eval_state", "sph_step",
     "sph_get_neighbors", "sph_get_hydro", "sph_get_grav", "sph_get_acc", "sph_get_octree", "sph_get_timings",
     "sph_get_dt", "sph_density_at", "sph_comm_unique_id", "sph_comm_init",
@@ -80,10 +80,15 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.sph_last_error.restype = C.c_char_p
         L.sph_last_error.argtypes = [C.c_void_p]
+        L.sph_launch_count.restype = C.c_int64
         for name in ABI_SYMBOLS:
             getattr(L, name)
         _lib = L
     return _lib
+
+
+def launch_count() -> int:
+    return int(lib().sph_launch_count())
 
 
 def device_count() -> int:

@@ -92,6 +92,9 @@ int sph_destroy(sph_handle *h);
 /* Message of the last failing call on this handle (h may be NULL: last error of sph_create). */
 const char *sph_last_error(const sph_handle *h);
 int sph_abi_version(void);
+/* Cumulative number of CUDA kernels this library has launched in the calling process (diagnostics; bench.py
+ * reports the per-step difference as gpu_launches). */
+int64_t sph_launch_count(void);
 /* Number of CUDA devices visible (0 = none; never an error).  */
 int sph_device_count(void);
 /* Run the handle's work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = own stream). */

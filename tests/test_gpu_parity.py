@@ -1,0 +1,303 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libsph_b200.so) against the CPU oracle on the same
+inputs, against the committed golden vectors, and - at the benchmark size - through size-independent properties.
+
+Tolerances (BASELINE.json north_star):
+    neighbour lists      bit-exact (index sequences and distances)
+    density, h           1e-9 relative (h: exact)
+    hydro acceleration   |da_i| <= 1e-9 * max(|a_i|, 1e-3 * S_i),  S_i = sum_j |pair term|  (cancellation guard)
+    tree gravity g, PHI  1e-6 relative at equal theta on the identical tree geometry
+    dt                   1e-9 relative
+"""
+import os
+
+import numpy as np
+import pytest
+from conftest import GOLDEN, make_case, oracle_kwargs, vec_rel
+
+pytestmark = pytest.mark.gpu
+
+TOL_SPH = 1e-9
+TOL_GRAV = 1e-6
+
+
+@pytest.fixture(scope="module")
+def sph():
+    from astrophysical_sph_b200 import libsph
+
+    if libsph.device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on a B200 (there is no CPU fallback)")
+    return libsph
+
+
+def vdw_scale(pos, vel, idx, r, h, poly):
+    """S_i = sum_j |v_ij| |gradW_ij|: the size of the terms whose signed sum is sum_vdw (cancellation guard)."""
+    from oracle import sph_numpy as NP
+
+    pos = np.asarray(pos); vel = np.asarray(vel)
+    j = idx - 1
+    d = pos[:, None, :] - pos[j]
+    v = vel[:, None, :] - vel[j]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gx, gy, gz = NP.gradW(d[..., 0], d[..., 1], d[..., 2], r, h, r / h[:, None], poly)
+    t = np.abs(v[..., 0] * gx) + np.abs(v[..., 1] * gy) + np.abs(v[..., 2] * gz)
+    return np.nan_to_num(t).sum(axis=1)
+
+
+def check_against_oracle(sph, O, eos, pos, vel, K, c, args, Kh=None, nthreads=None, check_tree=True):
+    Kh = Kh or c["Kh"]
+    N = pos.shape[0]
+    nthreads = nthreads or O.max_threads()
+    with sph.SphB200(N, Kh, eos, **args) as s:
+        out = s.eval_acc(pos, vel, K)
+        idx, r = s.neighbors()
+        hy = s.hydro()
+        g, phi = s.grav()
+        tree = s.octree() if check_tree else None
+        s.upload(pos, vel, K, 0.0)
+        s.eval_state()
+        dt = s.dt()
+    kw = oracle_kwargs(O, eos, c, K)
+    oh = O.hydro(pos, vel, c["m"], Kh, nthreads=nthreads, **kw)
+    l = np.abs(pos).max()
+    og, ophi, st = O.gravity(l, c["m"], pos, c["theta"], oh["h"], nthreads=nthreads)
+    # ---- neighbours: bit-exact
+    assert np.array_equal(idx, oh["idx"])
+    assert np.array_equal(r, oh["r"])
+    # ---- density / smoothing length
+    assert np.array_equal(hy["h"], oh["h"])
+    assert np.abs(hy["rho"] / oh["rho"] - 1).max() < TOL_SPH
+    # ---- hydro force, with the cancellation guard S_i ~ Kh * max pair term ~ |a| scale of the whole set
+    scale = np.linalg.norm(oh["ahyd"], axis=1)
+    floor = 1e-3 * np.median(scale)
+    assert vec_rel(hy["ahyd"], oh["ahyd"], floor) < TOL_SPH
+    # sum_j v_ij.gradW_ij is pure cancellation for e.g. solid-body rotation: compare against the summed term sizes
+    S = vdw_scale(pos, vel, oh["idx"], oh["r"], oh["h"], eos == "polytropic")
+    assert (np.abs(hy["sum_vdw"] - oh["sum_vdw"]) <= TOL_SPH * S + 1e-300).all()
+    assert np.array_equal(hy["mumax"], oh["mumax"])
+    if eos == "polytropic":
+        assert np.abs(hy["cs_i"] / oh["cs_i"] - 1).max() < TOL_SPH
+        dk = np.abs(oh["dkdt"]).max()
+        assert np.abs(hy["dkdt"] - oh["dkdt"]).max() <= TOL_SPH * max(dk, 1e-300)
+    # ---- tree + gravity
+    if check_tree:
+        otree = O.octree(l, c["m"], pos)
+        assert tree.shape == otree.shape
+        assert np.array_equal(tree[:, :10], otree[:, :10])          # Length, centre, bounds: bit-exact
+        assert np.array_equal(tree[:, 14:], otree[:, 14:])          # particle_count, depth (BFS order)
+        np.testing.assert_allclose(tree[:, 10:14], otree[:, 10:14], rtol=1e-12)   # Mass, rCOM
+    assert vec_rel(g, og, 1e-3 * np.median(np.linalg.norm(og, axis=1))) < TOL_GRAV
+    assert np.abs(phi / ophi - 1).max() < TOL_GRAV
+    oacc = oh["ahyd"] - c["G"] * og
+    assert vec_rel(out["acc"], oacc, 1e-3 * np.median(np.linalg.norm(oacc, axis=1))) < TOL_GRAV
+    assert np.abs(out["rho"] / oh["rho"] - 1).max() < TOL_SPH and np.array_equal(out["h"], oh["h"])
+    # ---- dt
+    odt = O.dt_from(vel, oacc, oh["rho"], oh["h"], oh["sum_vdw"], oh["mumax"], c["m"], eos=kw["eos"], cs=kw["cs"],
+                    cs_i=oh["cs_i"], alpha=c["alpha"], beta=c["beta"])
+    assert dt == pytest.approx(odt, rel=1e-9)
+    return st
+
+
+@pytest.mark.parametrize("eos", ["isothermal", "polytropic"])
+def test_config0_gaussian_sphere_5000(sph, oracle, eos):
+    """BASELINE.json configs[0]: gaussian_sphere, N=5000 default iniconds (README example R)."""
+    pos, vel, K, c, args = make_case(eos, "gaussian_sphere", 5000, R=5.38552341e16)
+    check_against_oracle(sph, oracle, eos, pos, vel, K, c, args)
+
+
+@pytest.mark.parametrize("eos", ["isothermal", "polytropic"])
+def test_moving_particles_exercise_viscosity(sph, oracle, eos):
+    pos, vel, K, c, args = make_case(eos, "gaussian_sphere", 3000, R=5.38552341e16, seed=3)
+    rng = np.random.default_rng(9)
+    vel = np.asfortranarray(3e7 * rng.standard_normal(vel.shape) - 3e-10 * pos)     # converging + random
+    check_against_oracle(sph, oracle, eos, pos, vel, K, c, args)
+
+
+def test_config1_plummer_100k(sph, oracle):
+    """BASELINE.json configs[1]: sample_plummer_sphere polytropic N=100k (deepest tree: depth 19)."""
+    pos, vel, K, c, args = make_case("polytropic", "sample_plummer_sphere", 100_000)
+    st = check_against_oracle(sph, oracle, "polytropic", pos, vel, K, c, args)
+    assert st[1] >= 17
+
+
+def test_boss_bodenheimer_100k(sph, oracle):
+    pos, vel, K, c, args = make_case("isothermal", "boss_bodenheimer", 100_000, T=10)
+    check_against_oracle(sph, oracle, "isothermal", pos, vel, K, c, args)
+
+
+def test_turbulent_cloud_50k(sph, oracle):
+    pos, vel, K, c, args = make_case("isothermal", "turbulent_molecular_cloud", 50_000, T=10)
+    check_against_oracle(sph, oracle, "isothermal", pos, vel, K, c, args, check_tree=False)
+
+
+@pytest.mark.parametrize("Kh", [2, 17, 96, 128])
+def test_neighbour_counts(sph, oracle, Kh):
+    """Kh from the minimum to beyond the 128-entry candidate buffer (second template instance)."""
+    pos, vel, K, c, args = make_case("isothermal", "gaussian_sphere", 2000, R=1.0, seed=5)
+    args.update(m=1.0 / 2000, cs=1.0, G=1.0)
+    c = dict(c, m=1.0 / 2000, cs=1.0, G=1.0, Kh=Kh)
+    with sph.SphB200(2000, Kh, "isothermal", **args) as s:
+        s.eval_acc(pos, vel)
+        idx, r = s.neighbors()
+    oidx, orr = oracle.knn(pos, pos, Kh, nthreads=4)
+    assert np.array_equal(idx, oidx) and np.array_equal(r, orr)
+
+
+def test_minimum_size_and_lattice_ties(sph, oracle):
+    """N = 64 (smallest accepted) on a cubic lattice: every distance is tied many times, particles sit exactly on
+    cell boundaries -> exercises tie-breaking by particle index and the strict `>` octant rule."""
+    g = np.arange(4, dtype=float) - 1.5
+    pos = np.asfortranarray(np.array(np.meshgrid(g, g, g, indexing="ij")).reshape(3, -1).T * 1.0)
+    vel = np.asfortranarray(np.zeros_like(pos))
+    N = pos.shape[0]
+    c = dict(m=1.0 / N, cs=1.0, G=1.0, theta=0.576, alpha=1.0, beta=2.0, Kh=20)
+    args = dict(m=c["m"], cs=1.0, G=1.0, theta=0.576, alpha=1.0, beta=2.0)
+    check_against_oracle(sph, oracle, "isothermal", pos, vel, None, c, args, Kh=20)
+    # larger lattice with points exactly at the origin planes (x - c > 0 is false there)
+    g = np.arange(9, dtype=float) - 4.0
+    pos = np.asfortranarray(np.array(np.meshgrid(g, g, g, indexing="ij")).reshape(3, -1).T * 0.25)
+    rng = np.random.default_rng(2)
+    pos = np.asfortranarray(pos[rng.permutation(pos.shape[0])])
+    N = pos.shape[0]
+    c["m"] = args["m"] = 1.0 / N
+    check_against_oracle(sph, oracle, "isothermal", pos, np.asfortranarray(np.zeros_like(pos)), None, c, args, Kh=20)
+
+
+def test_coincident_particles_are_reported(sph):
+    """The reference never returns on coincident particles (Appendix B-7); the library reports it."""
+    rng = np.random.default_rng(4)
+    pos = np.asfortranarray(rng.standard_normal((500, 3)))
+    pos[17] = pos[400]
+    vel = np.asfortranarray(np.zeros_like(pos))
+    with sph.SphB200(500, 20, "isothermal", m=1.0, cs=1.0, G=1.0) as s:
+        with pytest.raises(sph.SphError) as e:
+            s.eval_acc(pos, vel)
+        assert e.value.code == sph.SPH_ERR_TREE_DEPTH
+        # the handle stays usable
+        pos[17] += 1e-3
+        s.eval_acc(pos, vel)
+
+
+def test_call_sequence_errors(sph):
+    with sph.SphB200(200, 10, "polytropic", m=1.0, G=1.0) as s:
+        with pytest.raises(sph.SphError) as e:
+            s.step(1)
+        assert e.value.code == sph.SPH_ERR_STATE
+        with pytest.raises(sph.SphError):
+            s.neighbors()
+        rng = np.random.default_rng(0)
+        pos = np.asfortranarray(rng.standard_normal((200, 3)))
+        with pytest.raises(sph.SphError) as e:
+            s.eval_acc(pos, pos)            # polytropic needs K
+        assert e.value.code == sph.SPH_ERR_INVALID
+
+
+@pytest.mark.parametrize("name,eos", [("gauss_iso_1024.npz", "isothermal"), ("gauss_poly_1024.npz", "polytropic")])
+def test_golden_vectors_and_stepping(sph, name, eos):
+    """Committed fixtures (tests/golden/make_golden.py): one force evaluation and two full steps."""
+    z = np.load(os.path.join(GOLDEN, name))
+    m, cs, gamma, G, theta, alpha, beta, U, Kh = z["consts"]
+    Kh = int(Kh)
+    K = z["K"] if z["K"].size else None
+    N = z["pos"].shape[0]
+    with sph.SphB200(N, Kh, eos, m=m, cs=cs, gamma=gamma, G=G, theta=theta, alpha=alpha, beta=beta, U_iso=U) as s:
+        s.eval_acc(z["pos"], z["vel"], K)
+        idx, r = s.neighbors()
+        hy = s.hydro()
+        g, phi = s.grav()
+        assert np.array_equal(idx, z["idx"]) and np.array_equal(r[:, -1], z["rK"])
+        assert np.abs(hy["rho"] / z["rho"] - 1).max() < TOL_SPH
+        assert vec_rel(hy["ahyd"], z["ahyd"], 1e-3 * np.median(np.linalg.norm(z["ahyd"], axis=1))) < TOL_SPH
+        assert np.abs(hy["sum_vdw"] - z["sum_vdw"]).max() < TOL_SPH * np.abs(z["sum_vdw"]).max()
+        if eos == "polytropic":
+            assert np.abs(hy["dkdt"] - z["dkdt"]).max() < TOL_SPH * np.abs(z["dkdt"]).max()
+        assert vec_rel(g, z["g"]) < TOL_GRAV and np.abs(phi / z["phi"] - 1).max() < TOL_GRAV
+        # two iterations of the loop body (F/isothermal_sim.jl:152-213)
+        s.upload(z["pos"], z["vel"], K, 0.0)
+        info = s.step(len(z["dts"]))
+        p, v, Kend, t = s.download()
+    np.testing.assert_allclose(info["dts"], z["dts"], rtol=1e-9)
+    assert t == pytest.approx(float(z["t_end"]), rel=1e-9)
+    span = np.abs(z["pos"]).max()
+    assert np.abs(p - z["pos_end"]).max() < 1e-9 * span
+    assert vec_rel(v, z["vel_end"], 1e-3 * np.median(np.linalg.norm(z["vel_end"], axis=1))) < 1e-6
+    st, so = info["stats"], z["stats"]
+    np.testing.assert_allclose(st[:, :5], so[:, :5], rtol=1e-9, atol=0)       # t, T, V, U, Etot
+    assert np.abs(st[:, 5:8] - so[:, 5:8]).max() < 1e-9 * span                # centre of mass
+    pscale = m * np.abs(z["vel"]).sum()
+    assert np.abs(st[:, 8] - so[:, 8]).max() < 1e-9 * pscale                  # |p|
+    np.testing.assert_allclose(st[:, 9], so[:, 9], rtol=1e-7)                 # |L|
+    if eos == "polytropic":
+        np.testing.assert_allclose(Kend, z["K_end"], rtol=1e-9)
+
+
+def test_three_steps_track_the_oracle(sph, oracle):
+    pos, vel, K, c, args = make_case("polytropic", "gaussian_sphere", 5000, R=5.38552341e16)
+    with sph.SphB200(5000, 50, "polytropic", **args) as s:
+        s.upload(pos, vel, K, 0.0)
+        info = s.step(3)
+        p, v, Kend, t = s.download()
+    oo = oracle.step(pos, vel, c["m"], 50, c["G"], c["theta"], 0.0, 3, nthreads=oracle.max_threads(),
+                     **oracle_kwargs(oracle, "polytropic", c, K))
+    np.testing.assert_allclose(info["dts"], oo["dts"], rtol=1e-9)
+    assert np.abs(p - oo["pos"]).max() < 1e-9 * np.abs(pos).max()
+    np.testing.assert_allclose(Kend, oo["K"], rtol=1e-9)
+    np.testing.assert_allclose(info["stats"][:, 1:5], oo["stats"][:, 1:5], rtol=1e-9)
+
+
+def test_density_at_points(sph, oracle):
+    """HJL.density_plot (F/isothermal_hydroKDTree.jl:291-297): 1000 points on the x axis through the COM."""
+    pos, vel, K, c, args = make_case("isothermal", "gaussian_sphere", 20_000, R=5.38552341e16)
+    R = c["R"]
+    xs = np.linspace(-R, R, 1000)
+    com = pos.mean(axis=0)
+    pts = np.asfortranarray(np.column_stack([xs + com[0], np.full(1000, com[1]), np.full(1000, com[2])]))
+    with sph.SphB200(20_000, 50, "isothermal", **args) as s:
+        s.upload(pos, vel, None, 0.0)
+        rho = s.density_at(pts)
+    orho = oracle.density_at(pts, pos, c["m"], 50, nthreads=4)
+    np.testing.assert_allclose(rho, orho, rtol=1e-9)
+
+
+def test_properties_at_benchmark_size(sph):
+    """BASELINE.json configs[2] (Boss-Bodenheimer, N = 1e6): properties that need no oracle run."""
+    N = 1_000_000
+    pos, vel, K, c, args = make_case("isothermal", "boss_bodenheimer", N, T=10)
+    with sph.SphB200(N, 50, "isothermal", **args) as s:
+        out = s.eval_acc(pos, vel)
+        idx, r = s.neighbors()
+        hy = s.hydro()
+        g, phi = s.grav()
+        out2 = s.eval_acc(pos, vel)
+    # neighbour lists: self first, ascending distances, h = r_K / 2, all entries valid and distinct per row
+    assert np.array_equal(idx[:, 0], np.arange(1, N + 1, dtype=np.int32))
+    assert (np.diff(r, axis=1) >= 0).all() and (r[:, 0] == 0).all()
+    assert np.array_equal(hy["h"], r[:, -1] / 2)
+    assert idx.min() >= 1 and idx.max() <= N
+    srt = np.sort(idx[::997], axis=1)
+    assert (np.diff(srt, axis=1) > 0).all()
+    # exactness spot check of the search on a sample of rows against a brute-force scan
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, N, 12):
+        d = pos - pos[i]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        best = np.argsort(d2, kind="stable")[:50]
+        assert np.array_equal(idx[i] - 1, best)
+    # total hydro force vanishes (pair antisymmetry), gravity nearly so (monopole approximation)
+    tot = hy["ahyd"].sum(axis=0)
+    assert np.abs(tot).max() < 1e-10 * np.abs(hy["ahyd"]).sum(axis=0).max()
+    assert np.linalg.norm(g.sum(axis=0)) < 1e-2 * np.linalg.norm(g, axis=1).sum()
+    # uniform sphere: density within a few per cent of M / V in the interior; PHI at the centre = -3/2 M/R
+    rad = np.linalg.norm(pos, axis=1)
+    Rcl = rad.max()
+    rho0 = N * c["m"] / (4 / 3 * np.pi * Rcl**3)
+    inner = rad < 0.7 * Rcl
+    assert abs(np.median(hy["rho"][inner]) / rho0 - 1) < 0.05
+    centre = rad < 0.05 * Rcl
+    assert abs(np.mean(phi[centre]) / (-1.5 * N * c["m"] / Rcl) - 1) < 0.02
+    # radial gravity inside a uniform sphere: g = M r / R^3 (the library returns +grad PHI without G)
+    mid = (rad > 0.3 * Rcl) & (rad < 0.6 * Rcl)
+    gr = (g[mid] * pos[mid]).sum(axis=1) / rad[mid]
+    assert abs(np.median(gr / (N * c["m"] * rad[mid] / Rcl**3)) - 1) < 0.05
+    # idempotence: a second evaluation reproduces the first (atomics reorder only the last bits)
+    assert np.array_equal(out["rho"], out2["rho"]) and np.array_equal(out["phi"], out2["phi"])
+    assert vec_rel(out2["acc"], out["acc"], 1e-3 * np.median(np.linalg.norm(out["acc"], axis=1))) < 1e-12
