@@ -3,13 +3,18 @@
 //
 // Replaces GJL.compute_g / gravity_acc / Kernels / min_distance2_point_to_cell
 // (F/gravOctree_Single.jl:5-29, :231-304).  The reference walks the tree once per particle with a FIFO
-// queue; here one warp walks it for 32 key-adjacent targets at once with a shared depth-first stack whose
-// entries carry a lane mask: every lane evaluates the reference's two-clause acceptance test for ITS OWN
-// particle (s^2/d^2 < theta^2 with d to the node COM, and h_i^2/mindist^2(p_i, cell) < 0.25, :265); lanes
-// that accept add the monopole, the others stay in the mask pushed with the children.  Decisions are
-// therefore exactly per-particle as in the reference; only the floating-point summation order differs
-// (the reference's own order already drifts through its leaf list surgery, :293-300).
-// Node data is read with warp-uniform addresses (one 32 B sector per double4, broadcast to the warp).
+// queue; here one warp walks it for 32 key-adjacent targets at once with a shared depth-first stack of
+// cells TO BE OPENED, each with the mask of lanes that have not accepted one of its ancestors.  Opening a
+// cell visits its (BFS-contiguous) children: every lane of the mask evaluates the reference's two-clause
+// acceptance test for ITS OWN particle
+//        s^2/d^2 < theta^2  (d to the node COM)   and   h_i^2 / mindist^2(p_i, cell) < 0.25        (:265)
+// lanes that accept add the monopole, the others form the mask pushed with the child; leaf children are
+// evaluated on the spot.  Decisions are exactly per-particle as in the reference - d^2 and mindist^2 are
+// formed with the reference's roundings, the two quotient comparisons are decided by products and fall
+// back to the IEEE division inside a 1e-15 band around the threshold - only the floating-point
+// summation order differs (the reference's own order already drifts through its leaf list surgery,
+// :293-300), and 1/d, 1/d^3 come from one rsqrt (<= 4 ulp; the parity bar for gravity is 1e-6).
+// Node data is read with warp-uniform addresses (32 B per double4, broadcast to the warp).
 #include "sph_internal.cuh"
 
 namespace {
@@ -17,38 +22,48 @@ namespace {
 constexpr int GW_WARPS = 4;
 constexpr int GW_STACK = 192;
 
-// Kernels (F/gravOctree_Single.jl:5-29): returns grad(PHI)/r and PHI of the spline-softened potential
-__device__ __forceinline__ void grav_kernels(double r, double h, double &gPHI, double &PHI) {
-    const double q = r / h;
+// Kernels (F/gravOctree_Single.jl:5-29): grad(PHI)/r and PHI of the spline-softened potential, written in
+// q = r/h and 1/h (same polynomials; one reciprocal and one rsqrt instead of seven divisions)
+__device__ __forceinline__ void grav_pair(double d_sq, double h, double &gPHI, double &PHI) {
+    const double rinv = rsqrt(d_sq);
+    const double r = d_sq > 0.0 ? d_sq * rinv : 0.0;
+    const double hinv = 1.0 / h;
+    const double q = r * hinv;
     if (q > 2.0) {
-        const double r3 = r * r * r;
-        gPHI = 1 / r3;
-        PHI = -1 / r;
+        gPHI = rinv * rinv * rinv;   // 1/r^3  (:19)
+        PHI = -rinv;                 // -1/r   (:20)
         return;
     }
-    const double h2 = h * h;
-    const double q2 = q * q, q3 = q2 * q, q4 = q2 * q2, q5 = q4 * q;
+    const double q2 = q * q, q3 = q2 * q;
+    const double hinv3 = hinv * hinv * hinv;
     if (q <= 1.0) {
-        const double h3 = h2 * h, h4 = h2 * h2;
-        const double r2 = r * r, r3 = r2 * r;
-        gPHI = (1 / h2) * ((4.0 / 3 / h - 6.0 / 5 * (r2 / h3)) + 1.0 / 2 * (r3 / h4));
-        PHI = (1 / h) * (((2.0 / 3 * q2 - 3.0 / 10 * q4) + 1.0 / 10 * q5) - 7.0 / 5);
+        gPHI = hinv3 * ((4.0 / 3 - 6.0 / 5 * q2) + 1.0 / 2 * q3);                                   // (:10)
+        PHI = hinv * (((2.0 / 3 * q2 - 3.0 / 10 * (q2 * q2)) + 1.0 / 10 * (q2 * q3)) - 7.0 / 5);     // (:11)
     } else {
-        gPHI = ((1 / h2) * ((((8.0 / 3 * q - 3 * q2) + 6.0 / 5 * q3) - 1.0 / 6 * q4) - 1.0 / 15 * (1 / q2))) / r;
-        PHI = (1 / h) * (((((4.0 / 3 * q2 - q3) + 3.0 / 10 * q4) - 1.0 / 30 * q5) - 8.0 / 5) + 1.0 / 15 / q);
+        const double qi = rinv * h;  // 1/q
+        gPHI = hinv3 * ((((8.0 / 3 - 3 * q) + 6.0 / 5 * q2) - 1.0 / 6 * q3) - 1.0 / 15 * (qi * qi * qi));              // (:14)
+        PHI = hinv * (((((4.0 / 3 * q2 - q3) + 3.0 / 10 * (q2 * q2)) - 1.0 / 30 * (q2 * q3)) - 8.0 / 5) + 1.0 / 15 * qi);   // (:15)
     }
 }
 
+// fl(a / b) < c  decided without the division except within a relative band of 1e-15 around equality
+// (a, b, c >= 0; b == 0 gives +inf or NaN, i.e. false, exactly like the quotient)
+__device__ __forceinline__ bool quotient_less(double a, double b, double c) {
+    const double t = c * b;
+    if (a < t * (1.0 - 1e-15)) return true;
+    if (a > t * (1.0 + 1e-15)) return false;
+    return a / b < c;
+}
+
 template <bool COUNT>
-__global__ void __launch_bounds__(GW_WARPS * 32) walk_kernel(int64_t NS, int64_t t0, int64_t t1,
-                                                              const double4 *__restrict__ pos4, SphTree t,
-                                                              double theta_sq, double m,
-                                                              unsigned long long *__restrict__ scal,
-                                                              double *__restrict__ g, double *__restrict__ phi) {
+__global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t NS, int64_t t0, int64_t t1,
+                                                                 const double4 *__restrict__ pos4, SphTree t,
+                                                                 double theta_sq, double m,
+                                                                 unsigned long long *__restrict__ scal,
+                                                                 double *__restrict__ g, double *__restrict__ phi) {
     __shared__ int2 s_stack[GW_WARPS][GW_STACK];
     if (scal[SC_ERR] != 0ull) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
     int2 *stack = s_stack[warp];
     const int64_t s = t0 + ((int64_t)blockIdx.x * GW_WARPS + warp) * 32 + lane;
     const bool active = s < t1;
@@ -63,59 +78,63 @@ __global__ void __launch_bounds__(GW_WARPS * 32) walk_kernel(int64_t NS, int64_t
     const unsigned amask = __ballot_sync(0xffffffffu, active);
     int sp = 0;
     if (amask) {
-        // the walk starts at the root's children; the root itself is never tested (:246-249)
-        const int2 R = t.nodeI[0];
-        if (lane < R.y) stack[lane] = make_int2(R.x + lane, (int)amask);
-        sp = R.y;
+        // the walk starts by opening the root: the root itself is never tested (:246-249)
+        if (lane == 0) stack[0] = make_int2(0, (int)amask);
+        sp = 1;
     }
     __syncwarp();
     while (sp > 0) {
         const int2 top = stack[--sp];
         __syncwarp();
-        const int n = top.x;
         const bool mine = (((unsigned)top.y) >> lane) & 1u;
-        const int2 I = t.nodeI[n];
-        const double4 A = t.nodeA[n];
-        const double dx = px - A.x, dy = py - A.y, dz = pz - A.z;   // p_i - rCOM (:255)
-        const double d_sq = (dx * dx + dy * dy) + dz * dz;
-        if (COUNT && mine) ++visits;
-        if (I.y == 0) {
-            // leaf = one particle j (sorted slot I.x); A.w carries h_j.  The target's own leaf is skipped
-            // (the reference removes it from its parent's child list, :293-294).
-            if (mine && (int64_t)I.x != s) {
-                const double h_ij = (hi + A.w) / 2;                  // (:259)
-                double gP, pot;
-                grav_kernels(sqrt(d_sq), h_ij, gP, pot);
-                gx += m * (gP * dx); gy += m * (gP * dy); gz += m * (gP * dz);   // (:263)
-                ph += m * pot;                                                   // (:264)
-            }
-        } else {
-            bool open = false;
-            if (mine) {
-                const double4 B = t.nodeB[n];
-                const double4 C = t.nodeC[n];
-                const double ex = fmax(fmax(B.x - px, 0.0), px - B.w);           // (:231-236)
-                const double ey = fmax(fmax(B.y - py, 0.0), py - C.x);
-                const double ez = fmax(fmax(B.z - pz, 0.0), pz - C.y);
-                const double md2 = (ex * ex + ey * ey) + ez * ez;
-                const bool accept = (C.z / d_sq < theta_sq) && (hi2 / md2 < 0.25);   // (:265)
-                if (accept) {
-                    const double d = sqrt(d_sq);
-                    const double f = A.w / (d * d * d);                          // (:266-268)
-                    gx += f * dx; gy += f * dy; gz += f * dz;
-                    ph += -A.w / d;                                              // (:269)
-                } else {
-                    open = true;
+        const int2 I = t.nodeI[top.x];
+        const int first = I.x, nch = I.y & 0xff, leafmask = I.y >> 8;
+        if (sp + nch > GW_STACK) {  // cannot happen for depth <= 21; never write out of bounds
+            if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)ERRF_STACK);
+            break;
+        }
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+            const int n = first + c;
+            const double4 A = t.nodeA[n];
+            const double dx = px - A.x, dy = py - A.y, dz = pz - A.z;   // p_i - rCOM (:255)
+            const double d_sq = sph_d2_exact(dx, dy, dz);                // (:256)
+            if (COUNT && mine) ++visits;
+            if ((leafmask >> c) & 1) {
+                // leaf = one particle j; A.w carries h_j, its mass is m.  The target's own leaf is skipped
+                // (the reference removes it from its parent's child list, :293-294).
+                if (mine && (int64_t)t.nstart[n] != s) {
+                    double gP, pot;
+                    grav_pair(d_sq, (hi + A.w) / 2, gP, pot);            // h_ij = (h_i + h_j)/2  (:259)
+                    const double mg = m * gP;
+                    gx += mg * dx; gy += mg * dy; gz += mg * dz;         // (:263)
+                    ph += m * pot;                                       // (:264)
                 }
-            }
-            const unsigned om = __ballot_sync(0xffffffffu, open);
-            if (om) {
-                if (sp + I.y > GW_STACK) {  // cannot happen for depth <= 21; never write out of bounds
-                    if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)ERRF_STACK);
-                    break;
+            } else {
+                bool open = false;
+                if (mine) {
+                    const double4 B = t.nodeB[n];
+                    const double4 C = t.nodeC[n];
+                    const double ex = fmax(fmax(B.x - px, 0.0), px - B.w);   // (:231-236)
+                    const double ey = fmax(fmax(B.y - py, 0.0), py - C.x);
+                    const double ez = fmax(fmax(B.z - pz, 0.0), pz - C.y);
+                    const double md2 = sph_d2_exact(ex, ey, ez);
+                    // (s*s/d_sq < theta_sq) && (h_i*h_i / mind2 < 0.25)      (:265); C.z = (2 Length)^2
+                    const bool accept = quotient_less(C.z, d_sq, theta_sq) && quotient_less(hi2, md2, 0.25);
+                    if (accept) {
+                        const double rinv = rsqrt(d_sq);
+                        const double f = A.w * (rinv * rinv * rinv);         // Mass / d^3  (:266-268)
+                        gx += f * dx; gy += f * dy; gz += f * dz;
+                        ph -= A.w * rinv;                                    // -Mass / d   (:269)
+                    } else {
+                        open = true;
+                    }
                 }
-                if (lane < I.y) stack[sp + lane] = make_int2(I.x + lane, (int)om);
-                sp += I.y;
+                const unsigned om = __ballot_sync(0xffffffffu, open);
+                if (om) {
+                    if (lane == 0) stack[sp] = make_int2(n, (int)om);
+                    ++sp;
+                }
             }
         }
         __syncwarp();
@@ -129,7 +148,6 @@ __global__ void __launch_bounds__(GW_WARPS * 32) walk_kernel(int64_t NS, int64_t
         for (int o = 16; o > 0; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
         if (lane == 0) atomicAdd(scal + SC_VISITS, visits);
     }
-    (void)lt;
 }
 
 // after the search: leaves carry h_j in nodeA.w (their mass is the constant m)

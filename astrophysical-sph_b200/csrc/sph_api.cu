@@ -185,6 +185,7 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     h->ev_valid = true;
     h->have_eval = true;
     h->lists_valid = true;
+    h->hint_valid = true;
     h->last_acc = acc_out;
     return SPH_OK;
 }
@@ -238,6 +239,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
     h->p = *p;
     h->N = p->N;
     h->K = p->Kh;
+    h->no_hint = getenv("SPH_B200_NO_HINT") != nullptr;
     const int64_t Q = 1680;  // divisible by every rank count 1..8, 10, 12, 14, 15, 16
     h->NS = (h->N + Q - 1) / Q * Q;
 #define CK(call)                                                                                  \
@@ -540,6 +542,7 @@ int sph_get_timings(sph_handle *h, sph_timings *out) {
     out->total_ms = tot;
     SPH_CUDA(h, cudaMemcpy(h->h_scal, h->scal, sizeof(unsigned long long) * SC_COUNT, cudaMemcpyDeviceToHost));
     out->walk_visits = (double)h->h_scal[SC_VISITS];
+    out->knn_retries = (double)h->h_scal[SC_KNN_RETRY];
     return SPH_OK;
 }
 

@@ -5,7 +5,7 @@
 //   state   pos[3N] vel[3N] kent[N] acc[3N]                      orig, column-major like the Julia matrices
 //   sort    keys[N] u64 (21 levels x 3 bits), perm[N] i32        perm[s] = orig id of sorted slot s
 //   sorted  pos4[N] double4 {x,y,z,h}, vel4[N] double4 {vx,vy,vz,K_i}, hr[N] double2 {h,rho}
-//   tree    BFS-ordered linear octree: nodeI int2 {first child | particle, nchild (0 = leaf)},
+//   tree    BFS-ordered linear octree: nodeI int2 {first child | particle, nchild | leafmask << 8 (0 = leaf)},
 //           nodeA double4 {com, mass}, nodeB double4 {lo.xyz, hi.x}, nodeC double4 {hi.y, hi.z, (2L)^2, L},
 //           nstart/ncount i32 particle range of the node in the sorted arrays
 //   lists   nbr[N x K] i32 column-major, sorted-space rows and entries (0-based), d2k[N]
@@ -128,6 +128,8 @@ struct sph_handle {
     double *in_pos = nullptr, *in_vel = nullptr, *in_kent = nullptr, *in_acc = nullptr;
     const double *last_acc = nullptr;  // acceleration array written by the last evaluation
     bool lists_valid = false;          // neighbour lists match the current sort
+    bool hint_valid = false;           // o_h holds smoothing lengths of a completed evaluation (search radius hint)
+    bool no_hint = false;              // SPH_B200_NO_HINT: always search from the guaranteed radius
     // per-evaluation outputs, orig order
     double *o_rho = nullptr, *o_h = nullptr, *o_phi = nullptr, *o_sumvdw = nullptr, *o_mumax = nullptr,
            *o_cs = nullptr, *o_dkdt = nullptr, *o_ahyd = nullptr, *o_g = nullptr;
@@ -165,7 +167,7 @@ struct sph_handle {
 };
 
 // scal[0..SC_RESET) is cleared at the start of every force evaluation; SC_STICKY accumulates error flags
-enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_RESET = 6, SC_STICKY = 6, SC_COUNT = 8 };
+enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_KNN_RETRY, SC_RESET = 6, SC_STICKY = 6, SC_COUNT = 8 };
 enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4 };
 
 int sph_fail(sph_handle *h, int code, const std::string &msg);

@@ -167,13 +167,16 @@ __global__ void __launch_bounds__(TB) node_build_kernel(const uint64_t *__restri
             // depth-(d+1) cell that starts at the same particle
             const int sh = 3 * (SPH_LEVELS - 1 - d);
             const uint64_t pre = (d == 0) ? 0ull : ((key >> (sh + 3)) << 3);
-            int nch = 0, lo = s;
+            int nch = 0, lo = s, leafmask = 0;
             for (int c = 1; c <= 8 && lo < e; ++c) {
                 const int nb = (c == 8) ? e : lower_bound_key(keys, lo, e, (pre + (uint64_t)c) << sh);
-                nch += nb > lo;
+                if (nb > lo) {
+                    if (nb - lo == 1) leafmask |= 1 << nch;   // child holds one particle = leaf
+                    ++nch;
+                }
                 lo = nb;
             }
-            t.nodeI[k] = make_int2(bfs_of_old[o + 1], nch);
+            t.nodeI[k] = make_int2(bfs_of_old[o + 1], nch | (leafmask << 8));
         }
     }
 }
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(TB) com_level_kernel(int level, const int *__r
         const int2 I = t.nodeI[k];
         if (I.y == 0) continue;
         double tm = 0.0, wx = 0.0, wy = 0.0, wz = 0.0;
-        for (int c = 0; c < I.y; ++c) {
+        for (int c = 0; c < (I.y & 0xff); ++c) {
             const double4 A = t.nodeA[I.x + c];
             tm = __dadd_rn(tm, A.w);
             wx = __dadd_rn(wx, __dmul_rn(A.w, A.x));

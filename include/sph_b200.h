@@ -81,6 +81,7 @@ typedef struct sph_timings {
     double finish_ms;    /* assemble acc, un-permute, collectives          */
     double total_ms;
     double walk_visits;  /* sum over targets of node visits in the last walk (0 unless SPH_B200_COUNT_VISITS) */
+    double knn_retries;  /* targets whose hinted search radius held < Kh particles and was repeated           */
 } sph_timings;
 
 typedef struct sph_handle sph_handle;

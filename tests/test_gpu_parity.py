@@ -291,7 +291,9 @@ def test_properties_at_benchmark_size(sph):
     Rcl = rad.max()
     rho0 = N * c["m"] / (4 / 3 * np.pi * Rcl**3)
     inner = rad < 0.7 * Rcl
-    assert abs(np.median(hy["rho"][inner]) / rho0 - 1) < 0.05
+    # the reference's estimator (Kh = 50 incl. the self term W(0), h = r_K/2) reads ~21 % high on a uniform medium:
+    # the self term alone is m W(0)/rho = 32/147
+    assert 0.12 < np.median(hy["rho"][inner]) / rho0 - 1 < 0.30
     centre = rad < 0.05 * Rcl
     assert abs(np.mean(phi[centre]) / (-1.5 * N * c["m"] / Rcl) - 1) < 0.02
     # radial gravity inside a uniform sphere: g = M r / R^3 (the library returns +grad PHI without G)
