@@ -55,6 +55,14 @@ __device__ __forceinline__ bool quotient_less(double a, double b, double c) {
     return a / b < c;
 }
 
+// max(max(lo - p, 0), p - hi)  (min_distance2_point_to_cell, :231-236) with compare/select instead of the
+// NaN-aware fmax sequence; lo <= hi, so at most one of the two differences is positive
+__device__ __forceinline__ double axis_dist(double lo, double hi, double p) {
+    const double a = lo - p, b = p - hi;
+    const double mx = a > b ? a : b;
+    return mx > 0.0 ? mx : 0.0;
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t NS, int64_t t0, int64_t t1,
                                                                  const double4 *__restrict__ pos4, SphTree t,
@@ -73,6 +81,8 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t NS, int6
         px = p.x; py = p.y; pz = p.z; hi = p.w;
     }
     const double hi2 = hi * hi;
+    const double h2x = 2.0 * hi * (1.0 + 1e-9);      // clause 2 is certainly true when mindist > h2x
+    const double th_lo = theta_sq * (1.0 - 1e-15), th_hi = theta_sq * (1.0 + 1e-15);
     double gx = 0.0, gy = 0.0, gz = 0.0, ph = 0.0;
     unsigned long long visits = 0;
     const unsigned amask = __ballot_sync(0xffffffffu, active);
@@ -104,8 +114,15 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t NS, int6
                 // leaf = one particle j; A.w carries h_j, its mass is m.  The target's own leaf is skipped
                 // (the reference removes it from its parent's child list, :293-294).
                 if (mine && (int64_t)t.nstart[n] != s) {
+                    const double h_ij = (hi + A.w) / 2;                  // (:259)
                     double gP, pot;
-                    grav_pair(d_sq, (hi + A.w) / 2, gP, pot);            // h_ij = (h_i + h_j)/2  (:259)
+                    if (d_sq > 4.0 * (h_ij * h_ij)) {                    // q > 2: Newtonian (:19-20)
+                        const double rinv = rsqrt(d_sq);
+                        gP = rinv * rinv * rinv;
+                        pot = -rinv;
+                    } else {
+                        grav_pair(d_sq, h_ij, gP, pot);
+                    }
                     const double mg = m * gP;
                     gx += mg * dx; gy += mg * dy; gz += mg * dz;         // (:263)
                     ph += m * pot;                                       // (:264)
@@ -113,14 +130,24 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t NS, int6
             } else {
                 bool open = false;
                 if (mine) {
-                    const double4 B = t.nodeB[n];
-                    const double4 C = t.nodeC[n];
-                    const double ex = fmax(fmax(B.x - px, 0.0), px - B.w);   // (:231-236)
-                    const double ey = fmax(fmax(B.y - py, 0.0), py - C.x);
-                    const double ez = fmax(fmax(B.z - pz, 0.0), pz - C.y);
-                    const double md2 = sph_d2_exact(ex, ey, ez);
-                    // (s*s/d_sq < theta_sq) && (h_i*h_i / mind2 < 0.25)      (:265); C.z = (2 Length)^2
-                    const bool accept = quotient_less(C.z, d_sq, theta_sq) && quotient_less(hi2, md2, 0.25);
+                    const double2 D = t.nodeD[n];    // {(2 Length)^2, radius of the cell about its COM}
+                    // clause 1: s*s/d_sq < theta_sq                                             (:265)
+                    bool accept;
+                    if (D.x < d_sq * th_lo) accept = true;
+                    else if (D.x > d_sq * th_hi) accept = false;
+                    else accept = D.x / d_sq < theta_sq;
+                    // clause 2: h_i*h_i / mind2 < 0.25, i.e. mindist > 2 h_i.  mindist >= d - radius proves it
+                    // for all but the cells within a few h_i; those evaluate the reference's expression.
+                    if (accept) {
+                        const double w = D.y + h2x;
+                        if (!(d_sq > w * w)) {
+                            const double4 B = t.nodeB[n];
+                            const double4 C = t.nodeC[n];
+                            const double ex = axis_dist(B.x, B.w, px), ey = axis_dist(B.y, C.x, py),
+                                         ez = axis_dist(B.z, C.y, pz);
+                            accept = quotient_less(hi2, sph_d2_exact(ex, ey, ez), 0.25);
+                        }
+                    }
                     if (accept) {
                         const double rinv = rsqrt(d_sq);
                         const double f = A.w * (rinv * rinv * rinv);         // Mass / d^3  (:266-268)

@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(HB) force_kernel(int64_t N, int64_t NS, int K,
         const double vdw = (vx * gx + vy * gy) + vz * gz;
         svdw += vdw;
         mmax = fmax(mmax, mu);
-        if (j == 0) continue;  // hydroCalculation and evolve_K! start at column 2 (:226, poly :301)
+        // hydroCalculation and evolve_K! start at column 2 (:226, poly :301): column 1 is the particle itself.
+        // (lists arrive unordered from the grouped search, so the self entry is recognised by its index)
+        if (nj == s) continue;
         double ct;
         if (!poly) ct = m * (prri + Pi / 2);                                 // iso :232
         else ct = m * ((prri + prr[nj]) + Pi) / 2;                           // poly :235

@@ -22,6 +22,8 @@
 #include "sph_internal.cuh"
 
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_kernel(int64_t N, int K
                                                               const double *__restrict__ qpts, int64_t qstride,
                                                               const int *__restrict__ perm, SphTree t,
                                                               const double *__restrict__ hint_h, double hint_fac2,
+                                                              const int *__restrict__ list,
                                                               unsigned long long *__restrict__ scal,
                                                               int *__restrict__ nbr, double *__restrict__ d2k,
                                                               double *__restrict__ d2_out) {
@@ -96,8 +99,12 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_kernel(int64_t N, int K
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     unsigned long long retries = 0;
 
+    // targets: the range [t0, t1), or - for the second pass of the tiled search - the listed slots
     const int64_t nwarps = (int64_t)gridDim.x * KNN_WARPS;
-    for (int64_t s = t0 + (int64_t)blockIdx.x * KNN_WARPS + warp; s < t1; s += nwarps) {
+    const int64_t ntargets = list ? (int64_t)scal[SC_KNN_RETRY] : t1 - t0;
+    for (int64_t it = (int64_t)blockIdx.x * KNN_WARPS + warp; it < ntargets; it += nwarps) {
+        const int64_t s = list ? (int64_t)list[it] : t0 + it;
+        if (s < 0 || (SELF && s >= N)) { if (lane == 0) atomicMax(scal + SC_KNN_DBG, 201ull); continue; }
         double qx, qy, qz;
         if (SELF) {
             const double4 q = pos4[s];
@@ -147,10 +154,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_kernel(int64_t N, int K
                     const int c = first + lane;
                     const double4 B = t.nodeB[c];
                     const double4 C = t.nodeC[c];
-                    double ax = fmax(fmax(B.x - qx, qx - B.w), 0.0);
-                    double ay = fmax(fmax(B.y - qy, qy - C.x), 0.0);
-                    double az = fmax(fmax(B.z - qz, qz - C.y), 0.0);
-                    ax = fmax(ax - eps, 0.0); ay = fmax(ay - eps, 0.0); az = fmax(az - eps, 0.0);
+                    // point-to-box distance per axis, shrunk by eps (compare/select instead of NaN-aware fmax)
+                    double ax = B.x - qx, bx = qx - B.w, ay = B.y - qy, by = qy - C.x, az = B.z - qz, bz = qz - C.y;
+                    ax = (ax > bx ? ax : bx) - eps; ay = (ay > by ? ay : by) - eps; az = (az > bz ? az : bz) - eps;
+                    ax = ax > 0.0 ? ax : 0.0; ay = ay > 0.0 ? ay : 0.0; az = az > 0.0 ? az : 0.0;
                     const double md2 = ax * ax + ay * ay + az * az;
                     pass = md2 * (1.0 - 1e-12) <= R2;
                     cstart = t.nstart[c];
@@ -209,7 +216,41 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_kernel(int64_t N, int K
         }
         __syncwarp();
     }
-    if (retries && lane == 0) atomicAdd(scal + SC_KNN_RETRY, retries);
+    if (!list && retries && lane == 0) atomicAdd(scal + SC_KNN_RETRY, retries);
+}
+
+// sph_get_neighbors: one warp per row orders the (possibly unordered) list by (distance, particle id) and writes
+// the reference's layout: N x K column-major, 1-based caller ids, ascending distance (F/isothermal_hydroKDTree.jl:131-142)
+template <int CAP>
+__global__ void __launch_bounds__(KNN_WARPS * 32) export_sorted_kernel(int64_t N, int K, const double4 *__restrict__ pos4,
+                                                                        const int *__restrict__ perm,
+                                                                        const int *__restrict__ nbr,
+                                                                        int *__restrict__ idx_out, double *__restrict__ r_out) {
+    __shared__ double s_d2[KNN_WARPS][CAP];
+    __shared__ int s_id[KNN_WARPS][CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *bd2 = s_d2[warp];
+    int *bid = s_id[warp];
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    for (int64_t s = (int64_t)blockIdx.x * KNN_WARPS + warp; s < N; s += (int64_t)gridDim.x * KNN_WARPS) {
+        const double4 q = pos4[s];
+        for (int j = lane; j < CAP; j += 32) {
+            if (j < K) {
+                const int nj = nbr[s + (int64_t)j * N];
+                const double4 p = pos4[nj];
+                bd2[j] = sph_d2_exact(q.x - p.x, q.y - p.y, q.z - p.z);
+                bid[j] = nj;
+            } else { bd2[j] = INF; bid[j] = -1; }
+        }
+        __syncwarp();
+        warp_bitonic<CAP>(bd2, bid, perm, lane);
+        const int64_t i = perm[s];
+        for (int j = lane; j < K; j += 32) {
+            if (idx_out) idx_out[i + (int64_t)j * N] = perm[bid[j]] + 1;
+            if (r_out) r_out[i + (int64_t)j * N] = sqrt(bd2[j]);
+        }
+        __syncwarp();
+    }
 }
 
 // density_plot (F/isothermal_hydroKDTree.jl:291-297): h = r_K/2, rho = m * sum_j W(r_j, h), columns in order
@@ -231,6 +272,270 @@ __global__ void point_density_kernel(int64_t M, int K, const double *__restrict_
     rho[i] = m * s;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Grouped search (used once a radius hint exists, i.e. from the second force evaluation on).
+//
+// One warp owns 8 key-adjacent targets; lane = (target t = lane & 7, quarter = lane >> 3).  Every target has
+// its own trial ball R_t = 1.1 * 2 h_prev and "core" ball 2 h_prev.  The warp walks the octree once for the
+// bounding box of the 8 balls, in key order, and merges the overlapping buckets (cells of <= 32 particles =
+// contiguous ranges of the sorted array) into runs; the runs are streamed through shared memory in chunks of
+// 32 (coalesced loads), and the four lanes of a target test one quarter of each chunk against the target's
+// ball (broadcast shared-memory reads), appending hits to the target's core or shell column.
+// A target whose ball held >= K particles owns its exact K nearest: core hits first, then the K - |core|
+// smallest shell hits (or, when particles moved inwards, the core minus its |core| - K largest) - a few
+// short min/max scans instead of a sort.  Lists are therefore emitted UNORDERED (the consumers only need the
+// set and r_K = max; sph_get_neighbors sorts rows on export), column-major so stores stay coalesced.
+// Targets whose ball held < K particles, overflowed a column, or whose box spans too many candidates are
+// queued for the warp-per-target kernel above, which restarts from the guaranteed radius: exactness never
+// depends on the hint.
+// ---------------------------------------------------------------------------------------------------
+constexpr int KG_WARPS = 4;
+constexpr int KG_T = 8;          // targets per warp
+constexpr int KG_CAPC = 64;      // core hits per target (expected: K)
+constexpr int KG_CAPS = 48;      // shell hits per target (expected: 0.331 K = 16.5 +- 4 for K = 50)
+constexpr int KG_RANGES = 128;
+constexpr int KG_MAXCAND = 2048;
+
+struct KgWarp {
+    double cd2[KG_CAPC][KG_T];
+    double sd2[KG_CAPS][KG_T];
+    int cid[KG_CAPC][KG_T];
+    int sid[KG_CAPS][KG_T];
+    double stage[2][3][32];
+    int2 ranges[KG_RANGES];
+    int2 stack[KNN_STACK];
+    int ccnt[KG_T], scnt[KG_T];
+};
+
+__global__ void __launch_bounds__(KG_WARPS * 32, 3) knn_group_kernel(int64_t N, int K, int64_t t0, int64_t t1,
+                                                                     const double4 *__restrict__ pos4,
+                                                                     const int *__restrict__ perm, SphTree t,
+                                                                     const double *__restrict__ hint_h, double hint_fac2,
+                                                                     unsigned long long *__restrict__ scal, int stats,
+                                                                     int *__restrict__ retry_list,
+                                                                     int *__restrict__ nbr, double *__restrict__ d2k) {
+    extern __shared__ __align__(16) unsigned char kg_smem_raw[];
+    if (scal[SC_ERR] != 0ull) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    KgWarp &sm = reinterpret_cast<KgWarp *>(kg_smem_raw)[warp];
+    const unsigned lt = (1u << lane) - 1u;
+    const int tl = lane & (KG_T - 1), sub = lane >> 3;
+    const double ldom = __longlong_as_double((long long)scal[SC_LDOM]);
+    const double eps = ldom * 1e-14;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+
+    const int64_t ngroups = (t1 - t0 + KG_T - 1) / KG_T;
+    for (int64_t grp = (int64_t)blockIdx.x * KG_WARPS + warp; grp < ngroups; grp += (int64_t)gridDim.x * KG_WARPS) {
+        const int64_t s = t0 + grp * KG_T + tl;
+        const bool active = s < t1;
+        double qx = 0, qy = 0, qz = 0, Rsq = -1.0, Csq = -1.0;
+        bool need_retry = false;
+        if (active) {
+            const double4 q = pos4[s];
+            qx = q.x; qy = q.y; qz = q.z;
+            const double hh = hint_h[perm[s]];
+            if (hh > 0.0 && hh < INF) { Csq = 4.0 * hh * hh; Rsq = Csq * hint_fac2; }
+            else need_retry = true;
+        }
+        if (lane < KG_T) { sm.ccnt[lane] = 0; sm.scnt[lane] = 0; }
+        // ---- bounding box of the 8 balls
+        const bool searching = active && !need_retry;
+        const double R = searching ? sqrt(Rsq) * (1.0 + 1e-12) + eps : 0.0;
+        double blo[3] = {searching ? qx - R : INF, searching ? qy - R : INF, searching ? qz - R : INF};
+        double bhi[3] = {searching ? qx + R : -INF, searching ? qy + R : -INF, searching ? qz + R : -INF};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {   // lanes with equal (lane & 7) hold the same target
+                blo[a] = fmin(blo[a], __shfl_xor_sync(0xffffffffu, blo[a], o));
+                bhi[a] = fmax(bhi[a], __shfl_xor_sync(0xffffffffu, bhi[a], o));
+            }
+        }
+        // ---- list the buckets that overlap the box, in key order, merging contiguous ones into runs
+        int nr = 0;
+        bool overflow = false;
+        if (__any_sync(0xffffffffu, searching)) {
+            int cur_start = 0, cur_count = 0, tot_run = 0;
+            int sp = 1;
+            if (lane == 0) sm.stack[0] = make_int2(0, 0);
+            __syncwarp();
+            while (sp > 0) {
+                const int2 top = sm.stack[--sp];
+                __syncwarp();
+                if (top.y > 0) {   // a bucket: particles [top.x, top.x + top.y)
+                    // boxes that span far too many particles (key-order jumps, sparse halo particles around a
+                    // dense core) are cheaper in the warp-per-target search: stop listing early
+                    tot_run += top.y;
+                    if (tot_run > KG_MAXCAND) { overflow = true; break; }
+                    if (cur_count > 0 && top.x == cur_start + cur_count) cur_count += top.y;
+                    else {
+                        if (cur_count > 0) {
+                            if (nr >= KG_RANGES) { overflow = true; break; }
+                            if (lane == 0) sm.ranges[nr] = make_int2(cur_start, cur_count);
+                            ++nr;
+                        }
+                        cur_start = top.x; cur_count = top.y;
+                    }
+                    continue;
+                }
+                const int2 I = t.nodeI[top.x];
+                const int nch = I.y & 0xff, first = I.x;
+                bool pass = false;
+                int cstart = 0, ccount = 0;
+                if (lane < nch) {
+                    const int c = first + lane;
+                    const double4 B = t.nodeB[c];
+                    const double4 C = t.nodeC[c];
+                    pass = B.x <= bhi[0] && B.w >= blo[0] && B.y <= bhi[1] && C.x >= blo[1] && B.z <= bhi[2] && C.y >= blo[2];
+                    cstart = t.nstart[c];
+                    ccount = t.ncount[c];
+                }
+                // push in reverse so that the lowest child (smallest keys) is popped first
+                const unsigned pm = __ballot_sync(0xffffffffu, pass);
+                if (sp + __popc(pm) > KNN_STACK) {   // cannot happen for depth <= 21; never write out of bounds
+                    if (lane == 0) atomicMax(scal + SC_KNN_DBG, 101ull);
+                    overflow = true;
+                    break;
+                }
+                if (pass) {
+                    const int pos = sp + __popc(pm) - 1 - __popc(pm & lt);
+                    sm.stack[pos] = ccount <= KNN_BUCKET ? make_int2(cstart, ccount) : make_int2(first + lane, 0);
+                }
+                sp += __popc(pm);
+                __syncwarp();
+            }
+            if (!overflow && cur_count > 0) {
+                if (nr >= KG_RANGES) overflow = true;
+                else {
+                    if (lane == 0) sm.ranges[nr] = make_int2(cur_start, cur_count);
+                    ++nr;
+                }
+            }
+        }
+        __syncwarp();
+        {   // candidate volume of this group; boxes that span far too many particles (key-order jumps, sparse halo
+            // particles around a dense core) are cheaper in the warp-per-target search
+            int tot = 0;
+            bool bad = false;
+            for (int r = lane; r < nr; r += 32) {
+                const int2 rg = sm.ranges[r];
+                tot += rg.y;
+                bad = bad || rg.x < 0 || rg.y <= 0 || (int64_t)rg.x + rg.y > N;
+            }
+            if (__any_sync(0xffffffffu, bad)) {
+                if (lane == 0) atomicMax(scal + SC_KNN_DBG, 102ull);
+                overflow = true;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            if (tot > KG_MAXCAND) overflow = true;
+            if (stats && lane == 0) {
+                atomicAdd(scal + SC_KNN_CAND, (unsigned long long)tot);
+                atomicMax(scal + SC_KNN_MAXC, (unsigned long long)tot);
+                if (tot > KG_MAXCAND) atomicAdd(scal + SC_KNN_BIG, 1ull);
+            }
+        }
+        if (overflow) { need_retry = active; nr = 0; }
+        // ---- stream the candidates: the 4 lanes of a target share each chunk of 32
+        const double R2 = (searching && !overflow) ? Rsq : -1.0;
+        bool full = false;
+        int buf = 0;
+        for (int r = 0; r < nr; ++r) {
+            const int2 rg = sm.ranges[r];
+            for (int c0 = 0; c0 < rg.y; c0 += 32) {
+                const int nc = min(32, rg.y - c0);
+                double(*st)[32] = sm.stage[buf];
+                buf ^= 1;
+                if (lane < nc) {
+                    const double4 p = pos4[rg.x + c0 + lane];
+                    st[0][lane] = p.x; st[1][lane] = p.y; st[2][lane] = p.z;
+                }
+                __syncwarp();
+#pragma unroll 4
+                for (int k = sub; k < nc; k += 4) {
+                    const double d2 = sph_d2_exact(qx - st[0][k], qy - st[1][k], qz - st[2][k]);
+                    if (d2 <= R2) {
+                        if (d2 <= Csq) {
+                            const int slot = atomicAdd(&sm.ccnt[tl], 1);
+                            if (slot < KG_CAPC) { sm.cd2[slot][tl] = d2; sm.cid[slot][tl] = rg.x + c0 + k; }
+                            else full = true;
+                        } else {
+                            const int slot = atomicAdd(&sm.scnt[tl], 1);
+                            if (slot < KG_CAPS) { sm.sd2[slot][tl] = d2; sm.sid[slot][tl] = rg.x + c0 + k; }
+                            else full = true;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // any of the 4 lanes of a target saw an overflow?
+        full = full || __shfl_xor_sync(0xffffffffu, (int)full, 8);
+        full = full || __shfl_xor_sync(0xffffffffu, (int)full, 16);
+        const int c = min(sm.ccnt[tl], KG_CAPC), e = min(sm.scnt[tl], KG_CAPS);
+        if (searching && !overflow && (full || c + e < K)) need_retry = true;
+        // ---- selection by the first lane of each target: members = K smallest of core u shell by (d2, id)
+        int ncore = c < K ? c : K, nshell = K - ncore;
+        if (searching && !need_retry && sub == 0) {
+            if (c > K) {
+                // drop the c - K largest core hits: move them behind position K
+                for (int rdrop = 0; rdrop < c - K; ++rdrop) {
+                    const int last = c - 1 - rdrop;
+                    int bi = 0;
+                    double bd = sm.cd2[0][tl];
+                    int bid = sm.cid[0][tl];
+                    for (int i = 1; i <= last; ++i) {
+                        const double di = sm.cd2[i][tl];
+                        const int ii = sm.cid[i][tl];
+                        if (cand_less(bd, bid, di, ii, perm)) { bd = di; bid = ii; bi = i; }
+                    }
+                    sm.cd2[bi][tl] = sm.cd2[last][tl]; sm.cid[bi][tl] = sm.cid[last][tl];
+                    sm.cd2[last][tl] = bd; sm.cid[last][tl] = bid;
+                }
+            }
+            // take the nshell smallest shell hits to the front of the shell column
+            for (int rs = 0; rs < nshell; ++rs) {
+                int bi = rs;
+                double bd = sm.sd2[rs][tl];
+                int bid = sm.sid[rs][tl];
+                for (int i = rs + 1; i < e; ++i) {
+                    const double di = sm.sd2[i][tl];
+                    const int ii = sm.sid[i][tl];
+                    if (cand_less(di, ii, bd, bid, perm)) { bd = di; bid = ii; bi = i; }
+                }
+                sm.sd2[bi][tl] = sm.sd2[rs][tl]; sm.sid[bi][tl] = sm.sid[rs][tl];
+                sm.sd2[rs][tl] = bd; sm.sid[rs][tl] = bid;
+            }
+            // r_K^2 = largest member distance
+            double mx;
+            if (nshell > 0) mx = sm.sd2[nshell - 1][tl];
+            else {
+                mx = 0.0;
+                for (int i = 0; i < ncore; ++i) mx = fmax(mx, sm.cd2[i][tl]);
+            }
+            d2k[s] = mx;
+        }
+        __syncwarp();
+        // ---- emit (unordered): rows of 8 consecutive targets, 4 columns per store instruction
+        if (searching && !need_retry) {
+            for (int j = sub; j < K; j += 4)
+                nbr[s + (int64_t)j * N] = j < ncore ? sm.cid[j][tl] : sm.sid[j - ncore][tl];
+        }
+        // ---- queue the rest for the warp-per-target search
+        const unsigned rm = __ballot_sync(0xffffffffu, need_retry && sub == 0);
+        if (rm) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(scal + SC_KNN_RETRY, (unsigned long long)__popc(rm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (need_retry && sub == 0) {
+                if (base + __popc(rm & lt) >= (unsigned long long)N) atomicMax(scal + SC_KNN_DBG, 103ull);
+                else retry_list[base + __popc(rm & lt)] = (int)s;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 inline int knn_blocks(int64_t n) {
     int64_t blocks = (n + KNN_WARPS - 1) / KNN_WARPS;
     const int64_t cap = 148 * 8 * 4;
@@ -241,17 +546,57 @@ inline int knn_blocks(int64_t n) {
 
 cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1) {
     if (t1 <= t0) return cudaSuccess;
-    sph_note(1);
-    const int blocks = knn_blocks(t1 - t0);
     // radius hint: h of the previous evaluation (caller's particle order), valid once one evaluation completed
     const double *hint = (h->hint_valid && !h->no_hint) ? h->o_h : nullptr;
     const double fac2 = 1.1 * 1.1;
+    // the grouped search is opt-in (SPH_B200_KNN_GROUP=1): it is not yet faster than the warp-per-target search
+    static const bool warp_only = getenv("SPH_B200_KNN_GROUP") == nullptr;
+    if (hint && h->K <= KG_CAPC - 8 && !warp_only) {
+        // grouped search for the hinted targets, then the warp-per-target search for whatever it queued
+        static bool attr_set = false;
+        static const bool stats = getenv("SPH_B200_COUNT_VISITS") != nullptr;
+        const size_t smem = sizeof(KgWarp) * KG_WARPS;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(knn_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        sph_note(2);
+        const int64_t groups = (t1 - t0 + KG_T - 1) / KG_T;
+        int64_t blocks = (groups + KG_WARPS - 1) / KG_WARPS;
+        if (blocks > 148 * 3 * 8) blocks = 148 * 3 * 8;
+        knn_group_kernel<<<(int)blocks, KG_WARPS * 32, smem, h->stream>>>(
+            h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2, h->scal, (int)stats, h->cnt, h->nbr, h->d2k);
+        if (getenv("SPH_B200_TRACE")) {
+            cudaError_t e = cudaStreamSynchronize(h->stream);
+            unsigned long long sc[SC_COUNT];
+            cudaMemcpy(sc, h->scal, sizeof(sc), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[sph_b200 trace] group kernel done (%s): retry %llu cand %llu dbg %llu\n", cudaGetErrorString(e),
+                    sc[SC_KNN_RETRY], sc[SC_KNN_CAND], sc[SC_KNN_DBG]);
+        }
+        knn_kernel<128, true><<<148 * 5, KNN_WARPS * 32, 0, h->stream>>>(
+            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, nullptr, fac2, h->cnt, h->scal, h->nbr, h->d2k, nullptr);
+        return cudaGetLastError();
+    }
+    sph_note(1);
+    const int blocks = knn_blocks(t1 - t0);
     if (h->K <= 96)
         knn_kernel<128, true><<<blocks, KNN_WARPS * 32, 0, h->stream>>>(
-            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, fac2, h->scal, h->nbr, h->d2k, nullptr);
+            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, fac2, nullptr, h->scal, h->nbr, h->d2k, nullptr);
     else
         knn_kernel<256, true><<<blocks, KNN_WARPS * 32, 0, h->stream>>>(
-            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, fac2, h->scal, h->nbr, h->d2k, nullptr);
+            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, fac2, nullptr, h->scal, h->nbr, h->d2k, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t sph_launch_export_neighbors(sph_handle *h, int *idx_out_dev, double *r_out_dev) {
+    sph_note(1);
+    if (h->K <= 64)
+        export_sorted_kernel<64><<<148 * 8, KNN_WARPS * 32, 0, h->stream>>>(h->N, h->K, h->pos4, h->perm, h->nbr, idx_out_dev, r_out_dev);
+    else if (h->K <= 128)
+        export_sorted_kernel<128><<<148 * 8, KNN_WARPS * 32, 0, h->stream>>>(h->N, h->K, h->pos4, h->perm, h->nbr, idx_out_dev, r_out_dev);
+    else
+        export_sorted_kernel<256><<<148 * 8, KNN_WARPS * 32, 0, h->stream>>>(h->N, h->K, h->pos4, h->perm, h->nbr, idx_out_dev, r_out_dev);
     return cudaGetLastError();
 }
 
@@ -265,10 +610,10 @@ cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t 
     const int blocks = knn_blocks(M);
     if (h->K <= 96)
         knn_kernel<128, false><<<blocks, KNN_WARPS * 32, 0, h->stream>>>(
-            h->N, h->K, 0, M, h->pos4, pts_dev, M, h->perm, h->tree, nullptr, 1.0, h->scal, nullptr, nullptr, d2s);
+            h->N, h->K, 0, M, h->pos4, pts_dev, M, h->perm, h->tree, nullptr, 1.0, nullptr, h->scal, nullptr, nullptr, d2s);
     else
         knn_kernel<256, false><<<blocks, KNN_WARPS * 32, 0, h->stream>>>(
-            h->N, h->K, 0, M, h->pos4, pts_dev, M, h->perm, h->tree, nullptr, 1.0, h->scal, nullptr, nullptr, d2s);
+            h->N, h->K, 0, M, h->pos4, pts_dev, M, h->perm, h->tree, nullptr, 1.0, nullptr, h->scal, nullptr, nullptr, d2s);
     point_density_kernel<<<(int)((M + 127) / 128), 128, 0, h->stream>>>(M, h->K, d2s, h->p.m,
                                                                          h->p.eos == SPH_EOS_POLYTROPIC, rho_out_dev);
     e = cudaGetLastError();

@@ -59,22 +59,6 @@ cudaError_t dalloc(T **p, size_t n) {
 
 __global__ void sticky_kernel(unsigned long long *scal) { scal[SC_STICKY] |= scal[SC_ERR]; }
 
-__global__ void export_nbr_kernel(int64_t N, int K, const int *__restrict__ perm, const int *__restrict__ nbr,
-                                  const double4 *__restrict__ pos4, int *__restrict__ idx_out,
-                                  double *__restrict__ r_out) {
-    const int64_t tot = N * (int64_t)K;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t s = e % N, j = e / N;
-        const int nj = nbr[e];
-        const int64_t i = perm[s];
-        if (idx_out) idx_out[i + j * N] = perm[nj] + 1;  // 1-based, caller's particle ids
-        if (r_out) {
-            const double4 a = pos4[s], b = pos4[nj];
-            r_out[i + j * N] = sqrt(sph_d2_exact(a.x - b.x, a.y - b.y, a.z - b.z));
-        }
-    }
-}
-
 __global__ void export_tree_kernel(SphTree t, const unsigned long long *__restrict__ scal, double m, int64_t cap,
                                    double *__restrict__ out) {
     const int64_t M = min((int64_t)scal[SC_NNODES], cap);
@@ -110,6 +94,7 @@ int check_flags(sph_handle *h) {
                         h->stream) != cudaSuccess ||
         cudaStreamSynchronize(h->stream) != cudaSuccess)
         return sph_fail(h, SPH_ERR_CUDA, std::string("device error: ") + cudaGetErrorString(cudaGetLastError()));
+    if (h->h_scal[SC_KNN_DBG]) fprintf(stderr, "[sph_b200] KNN DEBUG CODE %llu\n", h->h_scal[SC_KNN_DBG]);
     const unsigned long long f = h->h_scal[SC_STICKY] | h->h_scal[SC_ERR];
     if (f) {
         cudaMemsetAsync(h->scal + SC_STICKY, 0, sizeof(unsigned long long), h->stream);
@@ -132,6 +117,8 @@ int nccl_fail(sph_handle *h, ncclResult_t r, const char *what) {
         if (r__ != ncclSuccess) return nccl_fail((h), r__, #call); \
     } while (0)
 
+#define TRACE(msg) do { if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[sph_b200 trace] %s (%s)\n", msg, cudaGetErrorString(cudaGetLastError())); } } while (0)
+
 // One getAcc on device arrays in the caller's particle order.
 int eval_internal(sph_handle *h, const double *pos, const double *vel, const double *kent, double *acc_out) {
     cudaStream_t st = h->stream;
@@ -143,21 +130,29 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     if (t1 > N) t1 = N;
     NcclApi &nc = nccl_api();
     ncclComm_t comm = (ncclComm_t)h->nccl;
+    static const bool trace = getenv("SPH_B200_TRACE") != nullptr;
 
     SPH_CUDA(h, cudaEventRecord(h->ev[0], st));
     SPH_CUDA(h, sph_launch_domain_keys(h, pos));
+    TRACE("sph_launch_domain_keys done");
     SPH_CUDA(h, sph_launch_permute(h, pos, vel, kent));
+    TRACE("sph_launch_permute done");
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_SORT + 1], st));
     SPH_CUDA(h, sph_launch_tree(h));
+    TRACE("sph_launch_tree done");
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_TREE + 1], st));
     SPH_CUDA(h, sph_launch_knn(h, t0, t1));
+    TRACE("sph_launch_knn done");
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_KNN + 1], st));
     SPH_CUDA(h, sph_launch_density(h, t0, t1));
+    TRACE("sph_launch_density done");
     if (multi)  // every rank needs h and rho of all particles (neighbours of its targets, leaf softening)
         SPH_NCCL(h, nc.AllGather(h->hr + h->rank * chunk, h->hr, (size_t)chunk * 2, ncclDouble, comm, st));
     SPH_CUDA(h, sph_launch_eos(h));
+    TRACE("sph_launch_eos done");
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_DENSITY + 1], st));
     SPH_CUDA(h, sph_launch_force(h, t0, t1));
+    TRACE("sph_launch_force done");
     if (multi) {
         // reactions a_j += ct*gradW land on particles of other ranks: sum the partial accelerations
         SPH_NCCL(h, nc.GroupStart());
@@ -169,6 +164,7 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     }
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_FORCE + 1], st));
     SPH_CUDA(h, sph_launch_walk(h, t0, t1));
+    TRACE("sph_launch_walk done");
     if (multi) {
         SPH_NCCL(h, nc.GroupStart());
         for (int k = 0; k < 3; ++k)
@@ -179,6 +175,7 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     }
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_GRAV + 1], st));
     SPH_CUDA(h, sph_launch_finish(h, acc_out));
+    TRACE("sph_launch_finish done");
     sph_note(1);
     sticky_kernel<<<1, 1, 0, st>>>(h->scal);
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_FINISH + 1], st));
@@ -276,7 +273,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
         if (const char *e = getenv("SPH_B200_NODE_FACTOR")) factor = atof(e) > 1.5 ? atof(e) : 3.0;
         t.cap = (int64_t)(factor * (double)N) + 1024;
         const size_t C = (size_t)t.cap;
-        CK(dalloc(&t.nodeI, C)); CK(dalloc(&t.nodeA, C)); CK(dalloc(&t.nodeB, C)); CK(dalloc(&t.nodeC, C));
+        CK(dalloc(&t.nodeI, C)); CK(dalloc(&t.nodeA, C)); CK(dalloc(&t.nodeB, C)); CK(dalloc(&t.nodeC, C)); CK(dalloc(&t.nodeD, C));
         CK(dalloc(&t.nstart, C)); CK(dalloc(&t.ncount, C)); CK(dalloc(&t.ndepth, C));
         CK(dalloc(&t.old_start, C)); CK(dalloc(&t.old_depth, C));
         CK(dalloc(&t.dkey_in, C)); CK(dalloc(&t.dkey_out, C)); CK(dalloc(&t.dval_in, C)); CK(dalloc(&t.dval_out, C));
@@ -308,7 +305,7 @@ int sph_destroy(sph_handle *h) {
                     h->o_g, h->keys, h->keys_alt, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->prr,
                     h->cs_s, h->d2k, h->nbr, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax, h->s_g, h->s_phi, h->cnt,
                     h->base, h->scal, h->stat_dev, h->red_partial, h->tree.nodeI, h->tree.nodeA, h->tree.nodeB,
-                    h->tree.nodeC, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
+                    h->tree.nodeC, h->tree.nodeD, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
                     h->tree.old_depth, h->tree.dkey_in, h->tree.dkey_out, h->tree.dval_in, h->tree.dval_out,
                     h->tree.bfs_of_old, h->tree.level_start};
     for (void *p : ptrs)
@@ -461,8 +458,7 @@ int sph_get_neighbors(sph_handle *h, int32_t *idx, double *r) {
         cudaFree(d_idx); cudaFree(d_r);
         return sph_fail(h, SPH_ERR_STATE, "sph_get_neighbors: only available on single-GPU handles");
     }
-    export_nbr_kernel<<<148 * 8, 256, 0, h->stream>>>(h->N, h->K, h->perm, h->nbr, h->pos4, d_idx, d_r);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = sph_launch_export_neighbors(h, d_idx, d_r);
     if (e == cudaSuccess && idx) e = cudaMemcpyAsync(idx, d_idx, NK * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && r) e = cudaMemcpyAsync(r, d_r, NK * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -543,6 +539,9 @@ int sph_get_timings(sph_handle *h, sph_timings *out) {
     SPH_CUDA(h, cudaMemcpy(h->h_scal, h->scal, sizeof(unsigned long long) * SC_COUNT, cudaMemcpyDeviceToHost));
     out->walk_visits = (double)h->h_scal[SC_VISITS];
     out->knn_retries = (double)h->h_scal[SC_KNN_RETRY];
+    if (getenv("SPH_B200_COUNT_VISITS"))
+        fprintf(stderr, "[sph_b200] knn tiles: candidates %llu, max/tile %llu, tiles over limit %llu, retries %llu\n",
+                h->h_scal[SC_KNN_CAND], h->h_scal[SC_KNN_MAXC], h->h_scal[SC_KNN_BIG], h->h_scal[SC_KNN_RETRY]);
     return SPH_OK;
 }
 

@@ -6,7 +6,7 @@
 //   sort    keys[N] u64 (21 levels x 3 bits), perm[N] i32        perm[s] = orig id of sorted slot s
 //   sorted  pos4[N] double4 {x,y,z,h}, vel4[N] double4 {vx,vy,vz,K_i}, hr[N] double2 {h,rho}
 //   tree    BFS-ordered linear octree: nodeI int2 {first child | particle, nchild | leafmask << 8 (0 = leaf)},
-//           nodeA double4 {com, mass}, nodeB double4 {lo.xyz, hi.x}, nodeC double4 {hi.y, hi.z, (2L)^2, L},
+//           nodeA double4 {com, mass}, nodeB double4 {lo.xyz, hi.x}, nodeC double4 {hi.y, hi.z, (2L)^2, L}, nodeD double2 {(2L)^2, max |corner - com|},
 //           nstart/ncount i32 particle range of the node in the sorted arrays
 //   lists   nbr[N x K] i32 column-major, sorted-space rows and entries (0-based), d2k[N]
 #pragma once
@@ -101,6 +101,7 @@ struct SphTree {
     int64_t cap = 0;  // node capacity
     int2 *nodeI = nullptr;
     double4 *nodeA = nullptr, *nodeB = nullptr, *nodeC = nullptr;
+    double2 *nodeD = nullptr;  // internal nodes: {(2 Length)^2, upper bound of the distance from rCOM to any point of the cell}
     int *nstart = nullptr, *ncount = nullptr, *ndepth = nullptr;
     // build scratch
     int *old_start = nullptr, *old_depth = nullptr;  // node list in (start, depth) order
@@ -167,7 +168,8 @@ struct sph_handle {
 };
 
 // scal[0..SC_RESET) is cleared at the start of every force evaluation; SC_STICKY accumulates error flags
-enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_KNN_RETRY, SC_RESET = 6, SC_STICKY = 6, SC_COUNT = 8 };
+enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_KNN_RETRY, SC_KNN_CAND, SC_KNN_BIG, SC_KNN_MAXC, SC_KNN_HITS, SC_KNN_DBG,
+       SC_RESET = 15, SC_STICKY = 15, SC_COUNT = 16 };
 enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4 };
 
 int sph_fail(sph_handle *h, int code, const std::string &msg);
@@ -199,6 +201,7 @@ cudaError_t sph_launch_tree(sph_handle *h);
 
 // ---- knn.cu --------------------------------------------------------------------------------------
 cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1);
+cudaError_t sph_launch_export_neighbors(sph_handle *h, int *idx_out_dev, double *r_out_dev);
 cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t M, double *rho_out_dev);
 
 // ---- hydro.cu ------------------------------------------------------------------------------------

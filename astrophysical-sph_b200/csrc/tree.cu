@@ -196,7 +196,14 @@ __global__ void __launch_bounds__(TB) com_level_kernel(int level, const int *__r
             wy = __dadd_rn(wy, __dmul_rn(A.w, A.y));
             wz = __dadd_rn(wz, __dmul_rn(A.w, A.z));
         }
-        t.nodeA[k] = make_double4(wx / tm, wy / tm, wz / tm, tm);
+        const double cx = wx / tm, cy = wy / tm, cz = wz / tm;
+        t.nodeA[k] = make_double4(cx, cy, cz, tm);
+        // radius of the cell about its COM (upper bound): lets the walk prove clause 2 of the acceptance test
+        // (h_i^2 / mindist^2 < 0.25) from d alone, since mindist >= d - radius
+        const double4 B = t.nodeB[k];
+        const double4 C = t.nodeC[k];
+        const double rx = fmax(cx - B.x, B.w - cx), ry = fmax(cy - B.y, C.x - cy), rz = fmax(cz - B.z, C.y - cz);
+        t.nodeD[k] = make_double2(C.z, sqrt(rx * rx + ry * ry + rz * rz) * (1.0 + 1e-12));
     }
 }
 

@@ -301,5 +301,5 @@ def test_properties_at_benchmark_size(sph):
     gr = (g[mid] * pos[mid]).sum(axis=1) / rad[mid]
     assert abs(np.median(gr / (N * c["m"] * rad[mid] / Rcl**3)) - 1) < 0.05
     # idempotence: a second evaluation reproduces the first (atomics reorder only the last bits)
-    assert np.array_equal(out["rho"], out2["rho"]) and np.array_equal(out["phi"], out2["phi"])
+    assert np.abs(out2["rho"] / out["rho"] - 1).max() < 1e-13 and np.abs(out2["phi"] / out["phi"] - 1).max() < 1e-12
     assert vec_rel(out2["acc"], out["acc"], 1e-3 * np.median(np.linalg.norm(out["acc"], axis=1))) < 1e-12
