@@ -112,7 +112,8 @@ def read_snapshot(filename):
     float64 (Matrix{Float64} layout), K is None when the column is empty."""
     import pandas as pd
 
-    df = pd.read_csv(filename, dtype={"type": str, "rlin": str, "rho_radial": str, "constants": str})
+    df = pd.read_csv(filename, dtype={"type": str, "rlin": str, "rho_radial": str, "constants": str},
+                     float_precision="round_trip")   # Julia parses Float64 text exactly; so must we
     part = df[df["type"] == "particle"]
     pos = np.asfortranarray(part[["x", "y", "z"]].to_numpy(dtype=np.float64))
     vel = np.asfortranarray(part[["vx", "vy", "vz"]].to_numpy(dtype=np.float64))
