@@ -22,12 +22,28 @@ namespace {
 constexpr int GW_WARPS = 4;
 constexpr int GW_STACK = 192;
 
+// 1/sqrt(x) and 1/x from the hardware seed (MUFU.RSQ64H / RCP64H, ~2^-22 relative) plus one Newton step each:
+// relative error <= 1e-13, five FP64 instructions instead of the IEEE sequences with their slow-path calls.
+// x must be a normal positive number (squared distances / smoothing lengths of distinct particles are).
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);          // 1 - x y^2
+    return fma(y * e, 0.5 + 0.375 * e, y);         // y (1 + e/2 + 3 e^2/8)
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y * e, 1.0 + e, y);                 // y (1 + e + e^2)
+}
+
 // Kernels (F/gravOctree_Single.jl:5-29): grad(PHI)/r and PHI of the spline-softened potential, written in
 // q = r/h and 1/h (same polynomials; one reciprocal and one rsqrt instead of seven divisions)
 __device__ __forceinline__ void grav_pair(double d_sq, double h, double &gPHI, double &PHI) {
-    const double rinv = rsqrt(d_sq);
-    const double r = d_sq > 0.0 ? d_sq * rinv : 0.0;
-    const double hinv = 1.0 / h;
+    const double rinv = d_sq > 0.0 ? fast_rsqrt(d_sq) : 0.0;
+    const double r = d_sq * rinv;
+    const double hinv = fast_rcp(h);
     const double q = r * hinv;
     if (q > 2.0) {
         gPHI = rinv * rinv * rinv;   // 1/r^3  (:19)
@@ -63,16 +79,25 @@ __device__ __forceinline__ double axis_dist(double lo, double hi, double p) {
     return mx > 0.0 ? mx : 0.0;
 }
 
+__device__ __forceinline__ int2 unpack_i2(double v) {
+    const long long b = __double_as_longlong(v);
+    return make_int2((int)(b & 0xffffffffLL), (int)(b >> 32));
+}
+__device__ __forceinline__ double pack_i2(int x, int y) {
+    return __longlong_as_double((long long)(unsigned)x | ((long long)y << 32));
+}
+
 template <bool COUNT>
-__global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t NS, int64_t t0, int64_t t1,
+__global__ void __launch_bounds__(GW_WARPS * 32, 6) walk_kernel(int64_t NS, int64_t t0, int64_t t1,
                                                                  const double4 *__restrict__ pos4, SphTree t,
                                                                  double theta_sq, double m,
                                                                  unsigned long long *__restrict__ scal,
                                                                  double *__restrict__ g, double *__restrict__ phi) {
-    __shared__ int2 s_stack[GW_WARPS][GW_STACK];
+    __shared__ int4 s_stack[GW_WARPS][GW_STACK];   // {first child, nch | leafmask << 8, lane mask, -}
     if (scal[SC_ERR] != 0ull) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int2 *stack = s_stack[warp];
+    int4 *stack = s_stack[warp];
+    const double4 *__restrict__ W = t.nodeW;
     const int64_t s = t0 + ((int64_t)blockIdx.x * GW_WARPS + warp) * 32 + lane;
     const bool active = s < t1;
     double px = 0, py = 0, pz = 0, hi = 1.0;
@@ -89,35 +114,37 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t NS, int6
     int sp = 0;
     if (amask) {
         // the walk starts by opening the root: the root itself is never tested (:246-249)
-        if (lane == 0) stack[0] = make_int2(0, (int)amask);
+        const int2 R = unpack_i2(W[1].z);
+        if (lane == 0) stack[0] = make_int4(R.x, R.y, (int)amask, 0);
         sp = 1;
     }
     __syncwarp();
     while (sp > 0) {
-        const int2 top = stack[--sp];
+        const int4 top = stack[--sp];
         __syncwarp();
-        const bool mine = (((unsigned)top.y) >> lane) & 1u;
-        const int2 I = t.nodeI[top.x];
-        const int first = I.x, nch = I.y & 0xff, leafmask = I.y >> 8;
+        const bool mine = (((unsigned)top.z) >> lane) & 1u;
+        const int first = top.x, nch = top.y & 0xff, leafmask = top.y >> 8;
         if (sp + nch > GW_STACK) {  // cannot happen for depth <= 21; never write out of bounds
             if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)ERRF_STACK);
             break;
         }
+        double4 A_next = W[2 * (int64_t)first], V_next = W[2 * (int64_t)first + 1];
 #pragma unroll 1
         for (int c = 0; c < nch; ++c) {
             const int n = first + c;
-            const double4 A = t.nodeA[n];
+            const double4 A = A_next, V = V_next;   // A = {rCOM, Mass | h_j}, V = {(2L)^2, radius, child info, range}
+            if (c + 1 < nch) { A_next = W[2 * (int64_t)n + 2]; V_next = W[2 * (int64_t)n + 3]; }   // children are contiguous
             const double dx = px - A.x, dy = py - A.y, dz = pz - A.z;   // p_i - rCOM (:255)
             const double d_sq = sph_d2_exact(dx, dy, dz);                // (:256)
             if (COUNT && mine) ++visits;
             if ((leafmask >> c) & 1) {
                 // leaf = one particle j; A.w carries h_j, its mass is m.  The target's own leaf is skipped
                 // (the reference removes it from its parent's child list, :293-294).
-                if (mine && (int64_t)t.nstart[n] != s) {
+                if (mine && (int64_t)unpack_i2(V.z).x != s) {
                     const double h_ij = (hi + A.w) / 2;                  // (:259)
                     double gP, pot;
                     if (d_sq > 4.0 * (h_ij * h_ij)) {                    // q > 2: Newtonian (:19-20)
-                        const double rinv = rsqrt(d_sq);
+                        const double rinv = fast_rsqrt(d_sq);
                         gP = rinv * rinv * rinv;
                         pot = -rinv;
                     } else {
@@ -130,16 +157,15 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t NS, int6
             } else {
                 bool open = false;
                 if (mine) {
-                    const double2 D = t.nodeD[n];    // {(2 Length)^2, radius of the cell about its COM}
                     // clause 1: s*s/d_sq < theta_sq                                             (:265)
                     bool accept;
-                    if (D.x < d_sq * th_lo) accept = true;
-                    else if (D.x > d_sq * th_hi) accept = false;
-                    else accept = D.x / d_sq < theta_sq;
+                    if (V.x < d_sq * th_lo) accept = true;
+                    else if (V.x > d_sq * th_hi) accept = false;
+                    else accept = V.x / d_sq < theta_sq;
                     // clause 2: h_i*h_i / mind2 < 0.25, i.e. mindist > 2 h_i.  mindist >= d - radius proves it
                     // for all but the cells within a few h_i; those evaluate the reference's expression.
                     if (accept) {
-                        const double w = D.y + h2x;
+                        const double w = V.y + h2x;
                         if (!(d_sq > w * w)) {
                             const double4 B = t.nodeB[n];
                             const double4 C = t.nodeC[n];
@@ -149,7 +175,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t NS, int6
                         }
                     }
                     if (accept) {
-                        const double rinv = rsqrt(d_sq);
+                        const double rinv = fast_rsqrt(d_sq);
                         const double f = A.w * (rinv * rinv * rinv);         // Mass / d^3  (:266-268)
                         gx += f * dx; gy += f * dy; gz += f * dz;
                         ph -= A.w * rinv;                                    // -Mass / d   (:269)
@@ -159,7 +185,10 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t NS, int6
                 }
                 const unsigned om = __ballot_sync(0xffffffffu, open);
                 if (om) {
-                    if (lane == 0) stack[sp] = make_int2(n, (int)om);
+                    if (lane == 0) {
+                        const int2 ci = unpack_i2(V.z);
+                        stack[sp] = make_int4(ci.x, ci.y, (int)om, 0);
+                    }
                     ++sp;
                 }
             }
@@ -177,13 +206,18 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t NS, int6
     }
 }
 
-// after the search: leaves carry h_j in nodeA.w (their mass is the constant m)
-__global__ void leaf_h_kernel(SphTree t, const double4 *__restrict__ pos4, const unsigned long long *__restrict__ scal) {
+// after the search: one 64-byte walk record per node (leaves carry h_j instead of their constant mass m)
+__global__ void pack_nodes_kernel(SphTree t, const double4 *__restrict__ pos4, const unsigned long long *__restrict__ scal) {
     if (scal[SC_ERR] != 0ull) return;
     const int64_t M = (int64_t)scal[SC_NNODES];
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < M; k += (int64_t)gridDim.x * blockDim.x) {
         const int2 I = t.nodeI[k];
-        if (I.y == 0) t.nodeA[k].w = pos4[I.x].w;
+        double4 A = t.nodeA[k];
+        double2 D = make_double2(0.0, 0.0);
+        if (I.y == 0) A.w = pos4[I.x].w;
+        else D = t.nodeD[k];
+        t.nodeW[2 * k] = A;
+        t.nodeW[2 * k + 1] = make_double4(D.x, D.y, pack_i2(I.x, I.y), pack_i2(t.nstart[k], t.ncount[k]));
     }
 }
 
@@ -191,7 +225,7 @@ __global__ void leaf_h_kernel(SphTree t, const double4 *__restrict__ pos4, const
 
 cudaError_t sph_launch_walk(sph_handle *h, int64_t t0, int64_t t1) {
     sph_note(1);
-    leaf_h_kernel<<<148 * 8, 256, 0, h->stream>>>(h->tree, h->pos4, h->scal);
+    pack_nodes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->tree, h->pos4, h->scal);
     if (t1 <= t0) return cudaGetLastError();
     sph_note(1);
     const int64_t nt = t1 - t0;

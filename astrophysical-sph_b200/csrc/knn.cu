@@ -360,7 +360,12 @@ __global__ void __launch_bounds__(KG_WARPS * 32, 3) knn_group_kernel(int64_t N, 
             if (lane == 0) sm.stack[0] = make_int2(0, 0);
             __syncwarp();
             while (sp > 0) {
-                const int2 top = sm.stack[--sp];
+                --sp;
+                // lane 0 reads the entry and broadcasts it: control flow below depends on it and must be warp-uniform
+                int2 top = make_int2(0, 0);
+                if (lane == 0) { const volatile int *e = (const volatile int *)&sm.stack[sp]; top.x = e[0]; top.y = e[1]; }
+                top.x = __shfl_sync(0xffffffffu, top.x, 0);
+                top.y = __shfl_sync(0xffffffffu, top.y, 0);
                 __syncwarp();
                 if (top.y > 0) {   // a bucket: particles [top.x, top.x + top.y)
                     // boxes that span far too many particles (key-order jumps, sparse halo particles around a
@@ -378,8 +383,18 @@ __global__ void __launch_bounds__(KG_WARPS * 32, 3) knn_group_kernel(int64_t N, 
                     }
                     continue;
                 }
+                if (top.x < 0 || (unsigned long long)top.x >= scal[SC_NNODES]) {
+                    if (lane == 0) atomicMax(scal + SC_KNN_DBG, 104ull);
+                    overflow = true;
+                    break;
+                }
                 const int2 I = t.nodeI[top.x];
                 const int nch = I.y & 0xff, first = I.x;
+                if (first < 0 || (unsigned long long)(first + nch) > scal[SC_NNODES] || nch > 8) {
+                    if (lane == 0) atomicMax(scal + SC_KNN_DBG, 105ull);
+                    overflow = true;
+                    break;
+                }
                 bool pass = false;
                 int cstart = 0, ccount = 0;
                 if (lane < nch) {
@@ -528,9 +543,255 @@ __global__ void __launch_bounds__(KG_WARPS * 32, 3) knn_group_kernel(int64_t N, 
             if (lane == 0) base = atomicAdd(scal + SC_KNN_RETRY, (unsigned long long)__popc(rm));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (need_retry && sub == 0) {
-                if (base + __popc(rm & lt) >= (unsigned long long)N) atomicMax(scal + SC_KNN_DBG, 103ull);
+                if (base + __popc(rm & lt) >= (unsigned long long)N) { atomicMax(scal + SC_KNN_DBG, 103ull); atomicMax(scal + SC_KNN_HITS, base); atomicMax(scal + SC_KNN_BIG, (unsigned long long)rm); }
                 else retry_list[base + __popc(rm & lt)] = (int)s;
             }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Hinted search, four targets per warp (the default from the second force evaluation on).
+//
+// A warp owns 4 key-adjacent targets, each with its trial ball R_t = f * 2 h_prev (f = 1.06).  Lanes are
+// CANDIDATES, as in the warp-per-target kernel, but one tree walk (pruned against the bounding box of the 4
+// balls) serves all 4 targets, and the particles of the overlapping buckets are first expanded into a dense
+// shared-memory index list so that every test round has 32 busy lanes (buckets hold ~12 particles on average).
+// Each lane tests its candidate against the 4 balls and appends it to the matching buffers by ballot prefix.
+// A target whose ball held >= K particles (and fit its 96-entry buffer) owns its exact K nearest; they are
+// ordered by (d2, particle id) with a register bitonic network over shuffles (<= 64 hits) or a rank sort, and
+// stored straight to their sorted position.  Targets without a usable hint, with < K particles in the ball,
+// an overflowing buffer or tied distances are queued for the warp-per-target kernel, which restarts from the
+// guaranteed radius and breaks ties by particle id: exactness never depends on the hint.
+// ---------------------------------------------------------------------------------------------------
+constexpr int KQ_T = 4;
+constexpr int KQ_CAP = 96;
+constexpr int KQ_WARPS = 6;
+constexpr int KQ_BKS = 64;      // buckets gathered before a flush
+constexpr int KQ_CAND = 512;    // candidates gathered before a flush
+
+struct KqWarp {
+    double d2[KQ_T][KQ_CAP];
+    int id[KQ_T][KQ_CAP];
+    int2 bks[KQ_BKS];
+    int cand[KQ_CAND];
+    int stack[KNN_STACK];
+};
+
+// compare-exchange step of the register bitonic sort: keys are the bit patterns of non-negative doubles
+__device__ __forceinline__ void kq_cex(unsigned long long &k, int &v, unsigned long long ok, int ov, bool keep_small) {
+    const bool other_smaller = ok < k;
+    if (other_smaller == keep_small) { k = ok; v = ov; }
+}
+
+__global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, int K, int64_t t0, int64_t t1,
+                                                                    const double4 *__restrict__ pos4,
+                                                                    const int *__restrict__ perm, SphTree t,
+                                                                    const double *__restrict__ hint_h, double hint_fac2,
+                                                                    unsigned long long *__restrict__ scal,
+                                                                    int *__restrict__ retry_list,
+                                                                    int *__restrict__ nbr, double *__restrict__ d2k) {
+    __shared__ KqWarp s_w[KQ_WARPS];
+    if (scal[SC_ERR] != 0ull) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    KqWarp &sm = s_w[warp];
+    const double ldom = __longlong_as_double((long long)scal[SC_LDOM]);
+    const double eps = ldom * 1e-14;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+
+    const int64_t nquads = (t1 - t0 + KQ_T - 1) / KQ_T;
+    for (int64_t quad = (int64_t)blockIdx.x * KQ_WARPS + warp; quad < nquads; quad += (int64_t)gridDim.x * KQ_WARPS) {
+        const int64_t s0 = t0 + quad * KQ_T;
+        double qx[KQ_T], qy[KQ_T], qz[KQ_T], R2[KQ_T];
+        int cnt[KQ_T];
+        bool ok[KQ_T];       // target is being searched with a finite trial radius
+        double blo[3] = {INF, INF, INF}, bhi[3] = {-INF, -INF, -INF};
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < KQ_T; ++k) {
+            const int64_t s = s0 + k;
+            qx[k] = qy[k] = qz[k] = 0.0; R2[k] = -1.0; cnt[k] = 0; ok[k] = false;
+            if (s < t1) {
+                const double4 q = pos4[s];
+                qx[k] = q.x; qy[k] = q.y; qz[k] = q.z;
+                const double hh = hint_h[perm[s]];
+                if (hh > 0.0 && hh < INF) {
+                    R2[k] = 4.0 * hh * hh * hint_fac2;
+                    ok[k] = true; any = true;
+                    const double R = sqrt(R2[k]) * (1.0 + 1e-12) + eps;
+                    blo[0] = fmin(blo[0], q.x - R); blo[1] = fmin(blo[1], q.y - R); blo[2] = fmin(blo[2], q.z - R);
+                    bhi[0] = fmax(bhi[0], q.x + R); bhi[1] = fmax(bhi[1], q.y + R); bhi[2] = fmax(bhi[2], q.z + R);
+                }
+            }
+        }
+        // ---- one walk for the 4 balls (all values above are warp-uniform)
+        if (any) {
+            int sp = 1, nb = 0, ncand = 0;
+            if (lane == 0) sm.stack[0] = 0;
+            __syncwarp();
+            for (;;) {
+                const bool last = sp == 0;
+                // ---- flush: expand the gathered buckets into a dense candidate list and test it in rounds of 32
+                if (nb > 0 && (last || nb + 8 > KQ_BKS || ncand + 8 * KNN_BUCKET > KQ_CAND)) {
+                    // exclusive prefix of the bucket sizes (<= 64 buckets: two per lane)
+                    const int c0 = lane < nb ? sm.bks[lane].y : 0, c1 = lane + 32 < nb ? sm.bks[lane + 32].y : 0;
+                    int i0 = c0, i1 = c1;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int a0 = __shfl_up_sync(0xffffffffu, i0, o), a1 = __shfl_up_sync(0xffffffffu, i1, o);
+                        if (lane >= o) { i0 += a0; i1 += a1; }
+                    }
+                    const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+                    {
+                        const int st0 = lane < nb ? sm.bks[lane].x : 0, st1 = lane + 32 < nb ? sm.bks[lane + 32].x : 0;
+                        int *o0 = sm.cand + (i0 - c0), *o1 = sm.cand + (tot0 + i1 - c1);
+                        for (int i = 0; i < c0; ++i) o0[i] = st0 + i;
+                        for (int i = 0; i < c1; ++i) o1[i] = st1 + i;
+                    }
+                    __syncwarp();
+                    for (int base = 0; base < ncand; base += 32) {
+                        const bool v = base + lane < ncand;
+                        int j = 0;
+                        double px = 0.0, py = 0.0, pz = 0.0;
+                        if (v) {
+                            j = sm.cand[base + lane];
+                            const double4 p = pos4[j];
+                            px = p.x; py = p.y; pz = p.z;
+                        }
+#pragma unroll
+                        for (int k = 0; k < KQ_T; ++k) {
+                            const double d2 = sph_d2_exact(qx[k] - px, qy[k] - py, qz[k] - pz);
+                            const bool hit = v && d2 <= R2[k];
+                            const unsigned om = __ballot_sync(0xffffffffu, hit);
+                            if (om) {
+                                const int slot = cnt[k] + __popc(om & lt);
+                                if (hit && slot < KQ_CAP) { sm.d2[k][slot] = d2; sm.id[k][slot] = j; }
+                                cnt[k] += __popc(om);     // may exceed KQ_CAP: detected below
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    nb = 0; ncand = 0;
+                }
+                if (last) break;
+                const int n = sm.stack[--sp];
+                __syncwarp();
+                const int2 I = t.nodeI[n];
+                const int nch = I.y & 0xff, first = I.x;
+                bool pass = false;
+                int cstart = 0, ccount = 0;
+                if (lane < nch) {
+                    const int c = first + lane;
+                    const double4 B = t.nodeB[c];
+                    const double4 C = t.nodeC[c];
+                    pass = B.x <= bhi[0] && B.w >= blo[0] && B.y <= bhi[1] && C.x >= blo[1] && B.z <= bhi[2] && C.y >= blo[2];
+                    cstart = t.nstart[c];
+                    ccount = t.ncount[c];
+                }
+                const bool is_bucket = ccount <= KNN_BUCKET;
+                const unsigned bm = __ballot_sync(0xffffffffu, pass && is_bucket);
+                const unsigned im = __ballot_sync(0xffffffffu, pass && !is_bucket);
+                if (pass && !is_bucket) sm.stack[sp + __popc(im & lt)] = first + lane;
+                sp += __popc(im);
+                if (pass && is_bucket) sm.bks[nb + __popc(bm & lt)] = make_int2(cstart, ccount);
+                nb += __popc(bm);
+                int add = (pass && is_bucket) ? ccount : 0;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);   // children sit in lanes 0..7
+                ncand += __shfl_sync(0xffffffffu, add, 0);
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        // ---- per target: order the buffer, emit the first K, or queue for the warp-per-target search
+        unsigned retry_mask = 0;
+#pragma unroll
+        for (int k = 0; k < KQ_T; ++k) {
+            const int64_t s = s0 + k;
+            if (s >= t1) continue;
+            const int n = cnt[k];
+            if (!ok[k] || n < K || n > KQ_CAP) { retry_mask |= 1u << k; continue; }
+            const double *bd2 = sm.d2[k];
+            const int *bid = sm.id[k];
+            bool tie = false;
+            if (n <= 64) {
+                // register bitonic sort of 64 keys (element e = lane + 32 r), shuffles for the 5 low strides
+                unsigned long long k0 = lane < n ? (unsigned long long)__double_as_longlong(bd2[lane]) : ~0ull;
+                unsigned long long k1 = lane + 32 < n ? (unsigned long long)__double_as_longlong(bd2[lane + 32]) : ~0ull;
+                int v0 = lane < n ? bid[lane] : -1, v1 = lane + 32 < n ? bid[lane + 32] : -1;
+#pragma unroll
+                for (int kk = 2; kk <= 64; kk <<= 1) {
+#pragma unroll
+                    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                        if (jj == 32) {
+                            // partner of element e is e ^ 32: the lane's own other register; ascending overall (kk == 64)
+                            if (k1 < k0) { const unsigned long long tk = k0; k0 = k1; k1 = tk; const int tv = v0; v0 = v1; v1 = tv; }
+                        } else {
+                            const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, k0, jj), p1 = __shfl_xor_sync(0xffffffffu, k1, jj);
+                            const int w0 = __shfl_xor_sync(0xffffffffu, v0, jj), w1 = __shfl_xor_sync(0xffffffffu, v1, jj);
+                            const bool lower = (lane & jj) == 0;                 // this lane holds the lower index of the pair
+                            const bool up0 = kk == 64 || (lane & kk) == 0;       // element lane      : ascending block?
+                            const bool up1 = kk == 64 || ((lane + 32) & kk) == 0;  // element lane + 32 : ascending block?
+                            kq_cex(k0, v0, p0, w0, lower == up0);
+                            kq_cex(k1, v1, p1, w1, lower == up1);
+                        }
+                    }
+                }
+                // equal neighbouring keys = tied distances: let the exact tie-breaking path handle the target
+                const unsigned long long nx0 = __shfl_down_sync(0xffffffffu, k0, 1), nx1 = __shfl_down_sync(0xffffffffu, k1, 1);
+                const unsigned long long f1 = __shfl_sync(0xffffffffu, k1, 0);
+                const bool t0e = (lane < 31 ? nx0 : f1) == k0 && k0 != ~0ull;
+                const bool t1e = lane < 31 && nx1 == k1 && k1 != ~0ull;
+                tie = __any_sync(0xffffffffu, t0e || t1e);
+                if (!tie) {
+                    if (lane < K) nbr[s + (int64_t)lane * N] = v0;
+                    if (lane + 32 < K) nbr[s + (int64_t)(lane + 32) * N] = v1;
+                    if (lane == K - 1) d2k[s] = __longlong_as_double((long long)k0);
+                    if (lane + 32 == K - 1) d2k[s] = __longlong_as_double((long long)k1);
+                }
+            } else {
+                // rank sort: count the entries that precede each of the lane's three
+                unsigned long long e_k[KQ_CAP / 32];
+                int e_id[KQ_CAP / 32], e_rank[KQ_CAP / 32];
+#pragma unroll
+                for (int r = 0; r < KQ_CAP / 32; ++r) {
+                    const int e = lane + 32 * r;
+                    e_k[r] = e < n ? (unsigned long long)__double_as_longlong(bd2[e]) : ~0ull;
+                    e_id[r] = e < n ? bid[e] : -1;
+                    e_rank[r] = 0;
+                }
+                for (int j = 0; j < n; ++j) {
+                    const unsigned long long kj = (unsigned long long)__double_as_longlong(bd2[j]);
+#pragma unroll
+                    for (int r = 0; r < KQ_CAP / 32; ++r) e_rank[r] += kj < e_k[r];
+                }
+                // ranks are a permutation of 0..n-1 unless two keys are equal
+                int rs = 0;
+#pragma unroll
+                for (int r = 0; r < KQ_CAP / 32; ++r) rs += e_id[r] >= 0 ? e_rank[r] : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+                tie = rs != n * (n - 1) / 2;
+                if (!tie) {
+#pragma unroll
+                    for (int r = 0; r < KQ_CAP / 32; ++r) {
+                        if (e_id[r] >= 0 && e_rank[r] < K) {
+                            nbr[s + (int64_t)e_rank[r] * N] = e_id[r];
+                            if (e_rank[r] == K - 1) d2k[s] = __longlong_as_double((long long)e_k[r]);
+                        }
+                    }
+                }
+            }
+            if (tie) retry_mask |= 1u << k;
+        }
+        if (retry_mask) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(scal + SC_KNN_RETRY, (unsigned long long)__popc(retry_mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lane < KQ_T && ((retry_mask >> lane) & 1u))
+                retry_list[base + __popc(retry_mask & lt)] = (int)(s0 + lane);
         }
         __syncwarp();
     }
@@ -548,7 +809,22 @@ cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1) {
     if (t1 <= t0) return cudaSuccess;
     // radius hint: h of the previous evaluation (caller's particle order), valid once one evaluation completed
     const double *hint = (h->hint_valid && !h->no_hint) ? h->o_h : nullptr;
-    const double fac2 = 1.1 * 1.1;
+    double fac2 = 1.1 * 1.1;
+    static const double quad_fac = getenv("SPH_B200_KNN_FAC") ? atof(getenv("SPH_B200_KNN_FAC")) : 1.06;
+    static const bool quad_off = getenv("SPH_B200_KNN_WARP") != nullptr;
+    if (hint && h->K <= 64 && !quad_off && getenv("SPH_B200_KNN_GROUP") == nullptr) {
+        // 4 targets per warp for the hinted targets, then the warp-per-target search for whatever it queued
+        sph_note(2);
+        fac2 = quad_fac * quad_fac;
+        const int64_t quads = (t1 - t0 + KQ_T - 1) / KQ_T;
+        int64_t blocks = (quads + KQ_WARPS - 1) / KQ_WARPS;
+        if (blocks > 148 * 5 * 8) blocks = 148 * 5 * 8;
+        knn_quad_kernel<<<(int)blocks, KQ_WARPS * 32, 0, h->stream>>>(h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2,
+                                                                     h->scal, h->cnt, h->nbr, h->d2k);
+        knn_kernel<128, true><<<148 * 5, KNN_WARPS * 32, 0, h->stream>>>(
+            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, nullptr, fac2, h->cnt, h->scal, h->nbr, h->d2k, nullptr);
+        return cudaGetLastError();
+    }
     // the grouped search is opt-in (SPH_B200_KNN_GROUP=1): it is not yet faster than the warp-per-target search
     static const bool warp_only = getenv("SPH_B200_KNN_GROUP") == nullptr;
     if (hint && h->K <= KG_CAPC - 8 && !warp_only) {

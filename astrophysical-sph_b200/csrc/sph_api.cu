@@ -94,7 +94,7 @@ int check_flags(sph_handle *h) {
                         h->stream) != cudaSuccess ||
         cudaStreamSynchronize(h->stream) != cudaSuccess)
         return sph_fail(h, SPH_ERR_CUDA, std::string("device error: ") + cudaGetErrorString(cudaGetLastError()));
-    if (h->h_scal[SC_KNN_DBG]) fprintf(stderr, "[sph_b200] KNN DEBUG CODE %llu\n", h->h_scal[SC_KNN_DBG]);
+    if (h->h_scal[SC_KNN_DBG]) fprintf(stderr, "[sph_b200] KNN DEBUG CODE %llu base %llu rm %llx retry %llu\n", h->h_scal[SC_KNN_DBG], h->h_scal[SC_KNN_HITS], h->h_scal[SC_KNN_BIG], h->h_scal[SC_KNN_RETRY]);
     const unsigned long long f = h->h_scal[SC_STICKY] | h->h_scal[SC_ERR];
     if (f) {
         cudaMemsetAsync(h->scal + SC_STICKY, 0, sizeof(unsigned long long), h->stream);
@@ -273,7 +273,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
         if (const char *e = getenv("SPH_B200_NODE_FACTOR")) factor = atof(e) > 1.5 ? atof(e) : 3.0;
         t.cap = (int64_t)(factor * (double)N) + 1024;
         const size_t C = (size_t)t.cap;
-        CK(dalloc(&t.nodeI, C)); CK(dalloc(&t.nodeA, C)); CK(dalloc(&t.nodeB, C)); CK(dalloc(&t.nodeC, C)); CK(dalloc(&t.nodeD, C));
+        CK(dalloc(&t.nodeI, C)); CK(dalloc(&t.nodeA, C)); CK(dalloc(&t.nodeB, C)); CK(dalloc(&t.nodeC, C)); CK(dalloc(&t.nodeD, C)); CK(dalloc(&t.nodeW, 2 * C));
         CK(dalloc(&t.nstart, C)); CK(dalloc(&t.ncount, C)); CK(dalloc(&t.ndepth, C));
         CK(dalloc(&t.old_start, C)); CK(dalloc(&t.old_depth, C));
         CK(dalloc(&t.dkey_in, C)); CK(dalloc(&t.dkey_out, C)); CK(dalloc(&t.dval_in, C)); CK(dalloc(&t.dval_out, C));
@@ -305,7 +305,7 @@ int sph_destroy(sph_handle *h) {
                     h->o_g, h->keys, h->keys_alt, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->prr,
                     h->cs_s, h->d2k, h->nbr, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax, h->s_g, h->s_phi, h->cnt,
                     h->base, h->scal, h->stat_dev, h->red_partial, h->tree.nodeI, h->tree.nodeA, h->tree.nodeB,
-                    h->tree.nodeC, h->tree.nodeD, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
+                    h->tree.nodeC, h->tree.nodeD, h->tree.nodeW, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
                     h->tree.old_depth, h->tree.dkey_in, h->tree.dkey_out, h->tree.dval_in, h->tree.dval_out,
                     h->tree.bfs_of_old, h->tree.level_start};
     for (void *p : ptrs)

@@ -101,6 +101,7 @@ struct SphTree {
     int64_t cap = 0;  // node capacity
     int2 *nodeI = nullptr;
     double4 *nodeA = nullptr, *nodeB = nullptr, *nodeC = nullptr;
+    double4 *nodeW = nullptr;  // walk records, 2 x double4 per node: {com.xyz, mass | h_j}, {(2L)^2, radius, bits{first|slot, nch|leafmask<<8}, bits{nstart, ncount}}
     double2 *nodeD = nullptr;  // internal nodes: {(2 Length)^2, upper bound of the distance from rCOM to any point of the cell}
     int *nstart = nullptr, *ncount = nullptr, *ndepth = nullptr;
     // build scratch
