@@ -570,6 +570,7 @@ constexpr int KQ_CAP = 96;
 constexpr int KQ_WARPS = 6;
 constexpr int KQ_BKS = 64;      // buckets gathered before a flush
 constexpr int KQ_CAND = 512;    // candidates gathered before a flush
+constexpr int KQ_MAXCAND = 3072; // quads whose box spans more candidates (key-order jumps) go to the per-target search
 
 struct KqWarp {
     double d2[KQ_T][KQ_CAP];
@@ -628,13 +629,20 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
         }
         // ---- one walk for the 4 balls (all values above are warp-uniform)
         if (any) {
-            int sp = 1, nb = 0, ncand = 0;
+            int sp = 1, nb = 0, ncand = 0, tested = 0;
             if (lane == 0) sm.stack[0] = 0;
             __syncwarp();
             for (;;) {
                 const bool last = sp == 0;
                 // ---- flush: expand the gathered buckets into a dense candidate list and test it in rounds of 32
                 if (nb > 0 && (last || nb + 8 > KQ_BKS || ncand + 8 * KNN_BUCKET > KQ_CAND)) {
+                    tested += ncand;
+                    if (tested > KQ_MAXCAND) {
+                        // the box of these 4 targets straddles a jump of the key order: four small balls are cheaper
+#pragma unroll
+                        for (int k = 0; k < KQ_T; ++k) ok[k] = false;
+                        break;
+                    }
                     // exclusive prefix of the bucket sizes (<= 64 buckets: two per lane)
                     const int c0 = lane < nb ? sm.bks[lane].y : 0, c1 = lane + 32 < nb ? sm.bks[lane + 32].y : 0;
                     int i0 = c0, i1 = c1;
@@ -821,8 +829,10 @@ cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1) {
         if (blocks > 148 * 5 * 8) blocks = 148 * 5 * 8;
         knn_quad_kernel<<<(int)blocks, KQ_WARPS * 32, 0, h->stream>>>(h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2,
                                                                      h->scal, h->cnt, h->nbr, h->d2k);
+        // queued targets keep their own hinted ball (only the shared box was too wide); a failing hint falls back to
+        // the guaranteed radius inside the kernel
         knn_kernel<128, true><<<148 * 5, KNN_WARPS * 32, 0, h->stream>>>(
-            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, nullptr, fac2, h->cnt, h->scal, h->nbr, h->d2k, nullptr);
+            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, 1.1 * 1.1, h->cnt, h->scal, h->nbr, h->d2k, nullptr);
         return cudaGetLastError();
     }
     // the grouped search is opt-in (SPH_B200_KNN_GROUP=1): it is not yet faster than the warp-per-target search

@@ -265,6 +265,7 @@ def run_b200(args, rank, world, local_rank):
                            "achieved_gbs": round(ALG_BYTES_STEP * value / 1e9, 2),
                            "frac": round(ALG_BYTES_STEP * value / 1e9 / peak, 5)},
         "phases_last_eval": phases,
+        "knn_retries": tim.get("knn_retries"),
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -6,5 +6,5 @@ python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/bench_brief.json").read())
 print("value %.4g p-s/s  %.2f ms/step  e2e %.4g  launches %d" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"]))
-print({k: v["ms"] for k, v in d["phases_last_eval"].items()})
+print({k: v["ms"] for k, v in d["phases_last_eval"].items()}, "knn_retries", d.get("knn_retries"))
 PY
