@@ -88,18 +88,20 @@ __device__ __forceinline__ double pack_i2(int x, int y) {
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(GW_WARPS * 32, 6) walk_kernel(int64_t NS, int64_t t0, int64_t t1,
+__global__ void __launch_bounds__(GW_WARPS * 32, 6) walk_kernel(int64_t N, int nranks, int rank, int64_t chunk,
                                                                  const double4 *__restrict__ pos4, SphTree t,
                                                                  double theta_sq, double m,
                                                                  unsigned long long *__restrict__ scal,
-                                                                 double *__restrict__ g, double *__restrict__ phi) {
+                                                                 double *__restrict__ part /* [8][4][chunk] */) {
     __shared__ int4 s_stack[GW_WARPS][GW_STACK];   // {first child, nch | leafmask << 8, lane mask, -}
     if (scal[SC_ERR] != 0ull) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int4 *stack = s_stack[warp];
     const double4 *__restrict__ W = t.nodeW;
-    const int64_t s = t0 + ((int64_t)blockIdx.x * GW_WARPS + warp) * 32 + lane;
-    const bool active = s < t1;
+    // block b of this rank owns tile b * nranks + rank (tiles of 128 key-adjacent targets, dealt round-robin)
+    const int64_t local = (int64_t)blockIdx.x * (GW_WARPS * 32) + threadIdx.x;
+    const int64_t s = ((int64_t)blockIdx.x * nranks + rank) * (GW_WARPS * 32) + threadIdx.x;
+    const bool active = s < N;
     double px = 0, py = 0, pz = 0, hi = 1.0;
     if (active) {
         const double4 p = pos4[s];  // .w = h_i
@@ -112,10 +114,14 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 6) walk_kernel(int64_t NS, int6
     unsigned long long visits = 0;
     const unsigned amask = __ballot_sync(0xffffffffu, active);
     int sp = 0;
+    // the walk starts by opening the root: the root itself is never tested (:246-249).  The root's children are
+    // dealt to blockIdx.y: 8x more, 8x shorter work items (wave quantisation matters when a rank owns ~1 wave of
+    // tiles); the partial sums are added in child order by walk_reduce_kernel, so results stay deterministic.
+    const int rc = blockIdx.y;
+    const int2 R = unpack_i2(W[1].z);
+    if (rc >= (R.y & 0xff)) return;
     if (amask) {
-        // the walk starts by opening the root: the root itself is never tested (:246-249)
-        const int2 R = unpack_i2(W[1].z);
-        if (lane == 0) stack[0] = make_int4(R.x, R.y, (int)amask, 0);
+        if (lane == 0) stack[0] = make_int4(R.x + rc, 1 | ((((R.y >> 8) >> rc) & 1) << 8), (int)amask, 0);
         sp = 1;
     }
     __syncwarp();
@@ -196,13 +202,26 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 6) walk_kernel(int64_t NS, int6
         __syncwarp();
     }
     if (active) {
-        g[s] = gx; g[s + NS] = gy; g[s + 2 * NS] = gz;
-        phi[s] = ph - (m * (7.0 / 5) / hi);                                      // (:303)
+        double *out = part + (size_t)rc * 4 * chunk;
+        out[local] = gx; out[local + chunk] = gy; out[local + 2 * chunk] = gz;
+        out[local + 3 * chunk] = rc == 0 ? ph - (m * (7.0 / 5) / hi) : ph;        // (:303), once
     }
     if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
         if (lane == 0) atomicAdd(scal + SC_VISITS, visits);
+    }
+}
+
+// sum of the per-root-child partial results in child order -> this rank's section of walk_buf
+__global__ void walk_reduce_kernel(int64_t n4 /* 4 * chunk */, const double *__restrict__ part, const double4 *__restrict__ W,
+                                   const unsigned long long *__restrict__ scal, double *__restrict__ out) {
+    if (scal[SC_ERR] != 0ull) return;
+    const int nch = unpack_i2(W[1].z).y & 0xff;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < nch; ++c) s += part[(size_t)c * n4 + i];
+        out[i] = s;
     }
 }
 
@@ -223,20 +242,24 @@ __global__ void pack_nodes_kernel(SphTree t, const double4 *__restrict__ pos4, c
 
 }  // namespace
 
-cudaError_t sph_launch_walk(sph_handle *h, int64_t t0, int64_t t1) {
-    sph_note(1);
+cudaError_t sph_launch_walk(sph_handle *h) {
+    static_assert(GW_WARPS * 32 == 128, "walk tiles are 128 targets (finish_kernel and sph_comm_init assume it)");
+    sph_note(2);
     pack_nodes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->tree, h->pos4, h->scal);
-    if (t1 <= t0) return cudaGetLastError();
-    sph_note(1);
-    const int64_t nt = t1 - t0;
-    const int64_t blocks = (nt + GW_WARPS * 32 - 1) / (GW_WARPS * 32);
+    const int64_t tiles = (h->N + 127) / 128;
+    const int64_t blocks = (tiles - h->rank + h->nranks - 1) / h->nranks;   // tiles rank, rank + P, ...
+    if (blocks <= 0) return cudaGetLastError();
     const double th2 = h->p.theta * h->p.theta;
+    double *out = h->walk_buf + (size_t)h->rank * 4 * h->walk_chunk;
+    const dim3 grid((unsigned)blocks, 8);
+    sph_note(1);
     static const bool count = getenv("SPH_B200_COUNT_VISITS") != nullptr;
     if (count)
-        walk_kernel<true><<<(int)blocks, GW_WARPS * 32, 0, h->stream>>>(h->NS, t0, t1, h->pos4, h->tree, th2, h->p.m,
-                                                                        h->scal, h->s_g, h->s_phi);
+        walk_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+                                                                 th2, h->p.m, h->scal, h->walk_part);
     else
-        walk_kernel<false><<<(int)blocks, GW_WARPS * 32, 0, h->stream>>>(h->NS, t0, t1, h->pos4, h->tree, th2, h->p.m,
-                                                                         h->scal, h->s_g, h->s_phi);
+        walk_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+                                                                  th2, h->p.m, h->scal, h->walk_part);
+    walk_reduce_kernel<<<148 * 8, 256, 0, h->stream>>>(4 * h->walk_chunk, h->walk_part, h->tree.nodeW, h->scal, out);
     return cudaGetLastError();
 }

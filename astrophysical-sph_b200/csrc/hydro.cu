@@ -171,8 +171,7 @@ cudaError_t sph_launch_eos(sph_handle *h) {
 
 cudaError_t sph_launch_force(sph_handle *h, int64_t t0, int64_t t1) {
     const int64_t N = h->N;
-    cudaMemsetAsync(h->s_ahyd, 0, sizeof(double) * 3 * h->NS, h->stream);
-    cudaMemsetAsync(h->s_dkdt, 0, sizeof(double) * h->NS, h->stream);
+    cudaMemsetAsync(h->s_red, 0, sizeof(double) * 6 * h->NS, h->stream);
     if (t1 <= t0) return cudaGetLastError();
     sph_note(1);
     const int64_t nt = t1 - t0;

@@ -22,33 +22,50 @@ inline int grid_for(int64_t n) {
 // stat_dev layout
 enum { DV_T = 0, DV_DT = 1, DV_SUM = 2 /* 12 sums */, DV_L = 16 /* 3 sums */, DV_ROW = 20 /* 10 */ };
 
+// walk results of sorted slot s: tile = s / 128 went to rank tile % nranks as its (tile / nranks)-th tile
+__device__ __forceinline__ const double *walk_slot(const double *__restrict__ walk_buf, int nranks, int64_t wchunk, int64_t s) {
+    const int64_t tile = s >> 7;
+    return walk_buf + (size_t)(tile % nranks) * 4 * wchunk + (tile / nranks) * 128 + (s & 127);
+}
+
+// per evaluation: total acceleration and h in the caller's particle order (integrator, next search radius)
 __global__ void __launch_bounds__(IB) finish_kernel(int64_t N, int64_t NS, const int *__restrict__ perm,
-                                                     const double *__restrict__ s_ahyd, const double *__restrict__ s_g,
-                                                     const double2 *__restrict__ hr, const double *__restrict__ s_phi,
-                                                     const double *__restrict__ s_sumvdw, const double *__restrict__ s_mumax,
-                                                     const double *__restrict__ cs_s, const double *__restrict__ s_dkdt,
-                                                     double G, double *__restrict__ acc, double *__restrict__ o_ahyd,
-                                                     double *__restrict__ o_g, double *__restrict__ o_rho,
-                                                     double *__restrict__ o_h, double *__restrict__ o_phi,
-                                                     double *__restrict__ o_sumvdw, double *__restrict__ o_mumax,
-                                                     double *__restrict__ o_cs, double *__restrict__ o_dkdt) {
+                                                     const double *__restrict__ s_ahyd, const double *__restrict__ walk_buf,
+                                                     int nranks, int64_t wchunk, const double2 *__restrict__ hr, double G,
+                                                     double *__restrict__ acc, double *__restrict__ o_h) {
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = perm[s];
+        const double *w = walk_slot(walk_buf, nranks, wchunk, s);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            acc[i + k * N] = __dsub_rn(s_ahyd[s + k * NS], __dmul_rn(G, w[k * wchunk]));   // ax -= G * g[:, 1]  (F/isothermal_sim.jl:41-43)
+        o_h[i] = hr[s].x;
+    }
+}
+
+// on demand (getters): the remaining per-particle results in the caller's particle order
+__global__ void __launch_bounds__(IB) unpermute_kernel(int64_t N, int64_t NS, const int *__restrict__ perm,
+                                                        const double *__restrict__ s_red, const double *__restrict__ walk_buf,
+                                                        int nranks, int64_t wchunk, const double2 *__restrict__ hr,
+                                                        const double *__restrict__ cs_s, double *__restrict__ o_ahyd,
+                                                        double *__restrict__ o_g, double *__restrict__ o_rho,
+                                                        double *__restrict__ o_phi, double *__restrict__ o_sumvdw,
+                                                        double *__restrict__ o_mumax, double *__restrict__ o_cs,
+                                                        double *__restrict__ o_dkdt) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = perm[s];
+        const double *w = walk_slot(walk_buf, nranks, wchunk, s);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const double a = s_ahyd[s + k * NS], gg = s_g[s + k * NS];
-            o_ahyd[i + k * N] = a;
-            o_g[i + k * N] = gg;
-            acc[i + k * N] = __dsub_rn(a, __dmul_rn(G, gg));   // ax -= G * g[:, 1]  (F/isothermal_sim.jl:41-43)
+            o_ahyd[i + k * N] = s_red[s + k * NS];
+            o_g[i + k * N] = w[k * wchunk];
         }
-        const double2 a = hr[s];
-        o_h[i] = a.x;
-        o_rho[i] = a.y;
-        o_phi[i] = s_phi[s];
-        o_sumvdw[i] = s_sumvdw[s];
-        o_mumax[i] = s_mumax[s];
+        o_rho[i] = hr[s].y;
+        o_phi[i] = w[3 * wchunk];
+        o_dkdt[i] = s_red[s + 3 * NS];
+        o_sumvdw[i] = s_red[s + 4 * NS];
+        o_mumax[i] = s_red[s + 5 * NS];
         o_cs[i] = cs_s[s];
-        o_dkdt[i] = s_dkdt[s];
     }
 }
 
@@ -66,23 +83,28 @@ __device__ __forceinline__ double block_min(double v) {
 __global__ void dt_init_kernel(unsigned long long *scal) { scal[SC_DT] = 0x7ff0000000000000ull; }
 
 // dt = 0.3 * min(min 1/|div v|, min h/|v|, min sqrt(h/|a|), min h/(c + 1.2(alpha c + beta max_j mu)))
-__global__ void __launch_bounds__(IB) dt_kernel(int64_t N, const double *__restrict__ vel, const double *__restrict__ acc,
-                                                 const double *__restrict__ rho, const double *__restrict__ hh,
-                                                 const double *__restrict__ sumvdw, const double *__restrict__ mumax,
-                                                 const double *__restrict__ csv, double m, double alpha, double beta,
+// evaluated in the sorted order of the evaluation it follows (vel4 = the velocities that evaluation was given)
+__global__ void __launch_bounds__(IB) dt_kernel(int64_t N, int64_t NS, const double4 *__restrict__ vel4,
+                                                 const double *__restrict__ s_red, const double *__restrict__ walk_buf,
+                                                 int nranks, int64_t wchunk, const double2 *__restrict__ hr,
+                                                 const double *__restrict__ csv, double G, double m, double alpha, double beta,
                                                  unsigned long long *__restrict__ scal) {
     double best = __longlong_as_double(0x7ff0000000000000LL);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-        const double vx = vel[i], vy = vel[i + N], vz = vel[i + 2 * N];
-        const double ax = acc[i], ay = acc[i + N], az = acc[i + 2 * N];
-        const double vel_r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+        const double4 v = vel4[s];
+        const double *w = walk_slot(walk_buf, nranks, wchunk, s);
+        const double ax = __dsub_rn(s_red[s], __dmul_rn(G, w[0]));
+        const double ay = __dsub_rn(s_red[s + NS], __dmul_rn(G, w[wchunk]));
+        const double az = __dsub_rn(s_red[s + 2 * NS], __dmul_rn(G, w[2 * wchunk]));
+        const double vel_r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y)), __dmul_rn(v.z, v.z)));
         const double a_r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az)));
-        const double h = hh[i], c = csv[i];
-        const double abs_div_v = fabs(-(__dmul_rn(m, sumvdw[i])) / rho[i]);
+        const double2 hrs = hr[s];
+        const double h = hrs.x, c = csv[s];
+        const double abs_div_v = fabs(-(__dmul_rn(m, s_red[s + 4 * NS])) / hrs.y);
         const double c1 = 1 / abs_div_v;
         const double c2 = h / vel_r;
         const double c3 = sqrt(h / a_r);
-        const double c4 = h / __dadd_rn(c, __dmul_rn(1.2, __dadd_rn(__dmul_rn(alpha, c), __dmul_rn(beta, mumax[i]))));
+        const double c4 = h / __dadd_rn(c, __dmul_rn(1.2, __dadd_rn(__dmul_rn(alpha, c), __dmul_rn(beta, s_red[s + 5 * NS]))));
         best = fmin(best, fmin(fmin(c1, c2), fmin(c3, c4)));
     }
     best = block_min(best);
@@ -113,18 +135,18 @@ __device__ __forceinline__ void block_sum_store(double (&v)[NV], double *__restr
 
 // sums: 0 sum |v|^2, 1 sum PHI, 2-4 sum pos, 5-7 sum vel, 8 sum K/(gamma-1) rho^(gamma-1)
 __global__ void __launch_bounds__(IB) stats1_kernel(int64_t N, const double *__restrict__ pos, const double *__restrict__ vel,
-                                                     const double *__restrict__ phi, const double *__restrict__ rho,
-                                                     const double *__restrict__ kent, double gamma,
-                                                     double *__restrict__ partial) {
+                                                     const double *__restrict__ walk_buf, int nranks, int64_t wchunk,
+                                                     const double2 *__restrict__ hr, const double4 *__restrict__ vel4, int poly,
+                                                     double gamma, double *__restrict__ partial) {
     double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         const double vx = vel[i], vy = vel[i + N], vz = vel[i + 2 * N];
         const double vr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
         v[0] += __dmul_rn(vr, vr);
-        v[1] += phi[i];
+        v[1] += walk_slot(walk_buf, nranks, wchunk, i)[3 * wchunk];   // sums do not care about the order: slot i of the sorted arrays
         v[2] += pos[i]; v[3] += pos[i + N]; v[4] += pos[i + 2 * N];
         v[5] += vx; v[6] += vy; v[7] += vz;
-        if (kent) v[8] += kent[i] / (gamma - 1) * pow(rho[i], gamma - 1);
+        if (poly) v[8] += vel4[i].w / (gamma - 1) * pow(hr[i].y, gamma - 1);   // K_i and rho_i of sorted slot i
     }
     block_sum_store<9>(v, partial);
 }
@@ -204,12 +226,14 @@ __global__ void __launch_bounds__(IB) correct_kernel(int64_t n3, double *__restr
 __global__ void advance_time_kernel(double *dv) { dv[DV_T] = __dadd_rn(dv[DV_T], dv[DV_DT]); }   // t += dt (:212)
 
 // K .+= 1/2*(gamma-1) ./ rho.^(gamma-1) .* dK * dt   called with dt/2  (F/polytrope_hydroKDTree.jl:313-315)
-__global__ void __launch_bounds__(IB) evolve_k_kernel(int64_t N, double *__restrict__ kent, const double *__restrict__ rho,
-                                                       const double *__restrict__ dkdt, double gamma,
-                                                       const double *__restrict__ dv) {
+__global__ void __launch_bounds__(IB) evolve_k_kernel(int64_t N, double *__restrict__ kent, const int *__restrict__ perm,
+                                                       const double2 *__restrict__ hr, const double *__restrict__ s_dkdt,
+                                                       double gamma, const double *__restrict__ dv) {
     const double hdt = dv[DV_DT] / 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
-        kent[i] = __dadd_rn(kent[i], __dmul_rn(__dmul_rn(1.0 / 2 * (gamma - 1) / pow(rho[i], gamma - 1), dkdt[i]), hdt));
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = perm[s];
+        kent[i] = __dadd_rn(kent[i], __dmul_rn(__dmul_rn(1.0 / 2 * (gamma - 1) / pow(hr[s].y, gamma - 1), s_dkdt[s]), hdt));
+    }
 }
 
 __global__ void set_time_kernel(double *dv, double t) { dv[DV_T] = t; }
@@ -218,18 +242,28 @@ __global__ void set_time_kernel(double *dv, double t) { dv[DV_T] = t; }
 
 cudaError_t sph_launch_finish(sph_handle *h, double *acc_out) {
     sph_note(1);
-    finish_kernel<<<grid_for(h->N), IB, 0, h->stream>>>(h->N, h->NS, h->perm, h->s_ahyd, h->s_g, h->hr, h->s_phi,
-                                                         h->s_sumvdw, h->s_mumax, h->cs_s, h->s_dkdt, h->p.G, acc_out,
-                                                         h->o_ahyd, h->o_g, h->o_rho, h->o_h, h->o_phi, h->o_sumvdw,
-                                                         h->o_mumax, h->o_cs, h->o_dkdt);
+    finish_kernel<<<grid_for(h->N), IB, 0, h->stream>>>(h->N, h->NS, h->perm, h->s_ahyd, h->walk_buf, h->nranks, h->walk_chunk,
+                                                         h->hr, h->p.G, acc_out, h->o_h);
+    h->outputs_fresh = false;
     return cudaGetLastError();
 }
 
-cudaError_t sph_launch_dt(sph_handle *h, const double *vel, const double *acc) {
+// getters: un-permute the remaining results of the last evaluation once
+cudaError_t sph_launch_unpermute(sph_handle *h) {
+    if (h->outputs_fresh) return cudaSuccess;
+    sph_note(1);
+    unpermute_kernel<<<grid_for(h->N), IB, 0, h->stream>>>(h->N, h->NS, h->perm, h->s_red, h->walk_buf, h->nranks, h->walk_chunk,
+                                                            h->hr, h->cs_s, h->o_ahyd, h->o_g, h->o_rho, h->o_phi, h->o_sumvdw,
+                                                            h->o_mumax, h->o_cs, h->o_dkdt);
+    h->outputs_fresh = true;
+    return cudaGetLastError();
+}
+
+cudaError_t sph_launch_dt(sph_handle *h) {
     sph_note(3);
     dt_init_kernel<<<1, 1, 0, h->stream>>>(h->scal);
-    dt_kernel<<<RED_BLOCKS, IB, 0, h->stream>>>(h->N, vel, acc, h->o_rho, h->o_h, h->o_sumvdw, h->o_mumax, h->o_cs,
-                                                 h->p.m, h->p.alpha, h->p.beta, h->scal);
+    dt_kernel<<<RED_BLOCKS, IB, 0, h->stream>>>(h->N, h->NS, h->vel4, h->s_red, h->walk_buf, h->nranks, h->walk_chunk, h->hr,
+                                                 h->cs_s, h->p.G, h->p.m, h->p.alpha, h->p.beta, h->scal);
     dt_final_kernel<<<1, 1, 0, h->stream>>>(h->scal, h->stat_dev);
     return cudaGetLastError();
 }
@@ -237,8 +271,8 @@ cudaError_t sph_launch_dt(sph_handle *h, const double *vel, const double *acc) {
 cudaError_t sph_launch_stats(sph_handle *h, double *log_row) {
     const bool poly = h->p.eos == SPH_EOS_POLYTROPIC;
     sph_note(5);
-    stats1_kernel<<<RED_BLOCKS, IB, 0, h->stream>>>(h->N, h->pos, h->vel, h->o_phi, h->o_rho, poly ? h->kent : nullptr,
-                                                     h->p.gamma, h->red_partial);
+    stats1_kernel<<<RED_BLOCKS, IB, 0, h->stream>>>(h->N, h->pos, h->vel, h->walk_buf, h->nranks, h->walk_chunk, h->hr, h->vel4,
+                                                     poly, h->p.gamma, h->red_partial);
     final_sum_kernel<9><<<1, IB, 0, h->stream>>>(h->red_partial, RED_BLOCKS, h->stat_dev + DV_SUM);
     stats2_kernel<<<RED_BLOCKS, IB, 0, h->stream>>>(h->N, h->pos, h->vel, h->stat_dev, h->red_partial);
     final_sum_kernel<3><<<1, IB, 0, h->stream>>>(h->red_partial, RED_BLOCKS, h->stat_dev + DV_L);
@@ -262,7 +296,7 @@ cudaError_t sph_launch_correct(sph_handle *h) {
 
 cudaError_t sph_launch_evolve_k(sph_handle *h) {
     sph_note(1);
-    evolve_k_kernel<<<grid_for(h->N), IB, 0, h->stream>>>(h->N, h->kent, h->o_rho, h->o_dkdt, h->p.gamma, h->stat_dev);
+    evolve_k_kernel<<<grid_for(h->N), IB, 0, h->stream>>>(h->N, h->kent, h->perm, h->hr, h->s_dkdt, h->p.gamma, h->stat_dev);
     return cudaGetLastError();
 }
 

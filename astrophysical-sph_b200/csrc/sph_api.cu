@@ -155,23 +155,15 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     TRACE("sph_launch_force done");
     if (multi) {
         // reactions a_j += ct*gradW land on particles of other ranks: sum the partial accelerations
-        SPH_NCCL(h, nc.GroupStart());
-        SPH_NCCL(h, nc.AllReduce(h->s_ahyd, h->s_ahyd, (size_t)h->NS * 3, ncclDouble, ncclSum, comm, st));
-        SPH_NCCL(h, nc.AllReduce(h->s_dkdt, h->s_dkdt, (size_t)h->NS, ncclDouble, ncclSum, comm, st));
-        SPH_NCCL(h, nc.AllGather(h->s_sumvdw + h->rank * chunk, h->s_sumvdw, (size_t)chunk, ncclDouble, comm, st));
-        SPH_NCCL(h, nc.AllGather(h->s_mumax + h->rank * chunk, h->s_mumax, (size_t)chunk, ncclDouble, comm, st));
-        SPH_NCCL(h, nc.GroupEnd());
+        // (also carries sum_vdw and mumax of the owned targets: the other ranks hold zeros there)
+        SPH_NCCL(h, nc.AllReduce(h->s_red, h->s_red, (size_t)h->NS * 6, ncclDouble, ncclSum, comm, st));
     }
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_FORCE + 1], st));
-    SPH_CUDA(h, sph_launch_walk(h, t0, t1));
+    SPH_CUDA(h, sph_launch_walk(h));
     TRACE("sph_launch_walk done");
     if (multi) {
-        SPH_NCCL(h, nc.GroupStart());
-        for (int k = 0; k < 3; ++k)
-            SPH_NCCL(h, nc.AllGather(h->s_g + k * h->NS + h->rank * chunk, h->s_g + k * h->NS, (size_t)chunk,
-                                     ncclDouble, comm, st));
-        SPH_NCCL(h, nc.AllGather(h->s_phi + h->rank * chunk, h->s_phi, (size_t)chunk, ncclDouble, comm, st));
-        SPH_NCCL(h, nc.GroupEnd());
+        SPH_NCCL(h, nc.AllGather(h->walk_buf + (size_t)h->rank * 4 * h->walk_chunk, h->walk_buf, (size_t)4 * h->walk_chunk,
+                                 ncclDouble, comm, st));
     }
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_GRAV + 1], st));
     SPH_CUDA(h, sph_launch_finish(h, acc_out));
@@ -261,12 +253,15 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(dalloc(&h->keys, N)); CK(dalloc(&h->keys_alt, N)); CK(dalloc(&h->perm, N)); CK(dalloc(&h->perm_alt, N));
     CK(dalloc(&h->pos4, NS)); CK(dalloc(&h->vel4, NS)); CK(dalloc(&h->hr, NS)); CK(dalloc(&h->prr, NS));
     CK(dalloc(&h->cs_s, NS)); CK(dalloc(&h->d2k, NS)); CK(dalloc(&h->nbr, N * K));
-    CK(dalloc(&h->s_ahyd, 3 * NS)); CK(dalloc(&h->s_dkdt, NS)); CK(dalloc(&h->s_sumvdw, NS)); CK(dalloc(&h->s_mumax, NS));
-    CK(dalloc(&h->s_g, 3 * NS)); CK(dalloc(&h->s_phi, NS));
+    CK(dalloc(&h->s_red, 6 * NS));
+    h->s_ahyd = h->s_red; h->s_dkdt = h->s_red + 3 * NS; h->s_sumvdw = h->s_red + 4 * NS; h->s_mumax = h->s_red + 5 * NS;
+    h->walk_chunk = (int64_t)((N + 127) / 128) * 128;   // nranks = 1 until sph_comm_init
+    CK(dalloc(&h->walk_buf, 4 * ((size_t)h->walk_chunk + 128 * SPH_MAX_RANKS)));
+    CK(dalloc(&h->walk_part, 8 * 4 * (size_t)h->walk_chunk));
     CK(dalloc(&h->cnt, N + 1)); CK(dalloc(&h->base, N + 2));
     CK(cudaMemset(h->hr, 0, NS * sizeof(double2)));
-    CK(cudaMemset(h->s_sumvdw, 0, NS * 8)); CK(cudaMemset(h->s_mumax, 0, NS * 8));
-    CK(cudaMemset(h->s_g, 0, 3 * NS * 8)); CK(cudaMemset(h->s_phi, 0, NS * 8));
+    CK(cudaMemset(h->s_red, 0, 6 * NS * 8));
+    CK(cudaMemset(h->walk_buf, 0, 4 * ((size_t)h->walk_chunk + 128 * SPH_MAX_RANKS) * 8));
     {
         SphTree &t = h->tree;
         double factor = 3.0;
@@ -303,7 +298,7 @@ int sph_destroy(sph_handle *h) {
     void *ptrs[] = {h->pos, h->vel, h->kent, h->acc, h->pos_half, h->vel_half, h->in_pos, h->in_vel, h->in_kent,
                     h->in_acc, h->o_rho, h->o_h, h->o_phi, h->o_sumvdw, h->o_mumax, h->o_cs, h->o_dkdt, h->o_ahyd,
                     h->o_g, h->keys, h->keys_alt, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->prr,
-                    h->cs_s, h->d2k, h->nbr, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax, h->s_g, h->s_phi, h->cnt,
+                    h->cs_s, h->d2k, h->nbr, h->s_red, h->walk_buf, h->walk_part, h->cnt,
                     h->base, h->scal, h->stat_dev, h->red_partial, h->tree.nodeI, h->tree.nodeA, h->tree.nodeB,
                     h->tree.nodeC, h->tree.nodeD, h->tree.nodeW, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
                     h->tree.old_depth, h->tree.dkey_in, h->tree.dkey_out, h->tree.dval_in, h->tree.dval_out,
@@ -383,6 +378,7 @@ int sph_eval_acc(sph_handle *h, const double *pos, const double *vel, const doub
     SPH_CUDA(h, cudaMemcpyAsync(h->in_vel, vel, 3 * N * 8, cudaMemcpyHostToDevice, h->stream));
     if (poly) SPH_CUDA(h, cudaMemcpyAsync(h->in_kent, K, N * 8, cudaMemcpyHostToDevice, h->stream));
     if (int rc = eval_internal(h, h->in_pos, h->in_vel, poly ? h->in_kent : nullptr, h->in_acc)) return rc;
+    if (rho || phi) SPH_CUDA(h, sph_launch_unpermute(h));
     if (int rc = d2h(h, acc, h->in_acc, 3 * N)) return rc;
     if (int rc = d2h(h, rho, h->o_rho, N)) return rc;
     if (int rc = d2h(h, hsml, h->o_h, N)) return rc;
@@ -395,7 +391,7 @@ int sph_eval_state(sph_handle *h) {
     if (!h->have_state) return sph_fail(h, SPH_ERR_STATE, "sph_eval_state: no state uploaded");
     SPH_CUDA(h, cudaSetDevice(h->p.device));
     if (int rc = eval_internal(h, h->pos, h->vel, h->p.eos == SPH_EOS_POLYTROPIC ? h->kent : nullptr, h->acc)) return rc;
-    if (int rc = sph_launch_dt(h, h->vel, h->acc) != cudaSuccess ? SPH_ERR_CUDA : 0) return sph_fail(h, rc, "dt launch failed");
+    if (int rc = sph_launch_dt(h) != cudaSuccess ? SPH_ERR_CUDA : 0) return sph_fail(h, rc, "dt launch failed");
     return check_flags(h);
 }
 
@@ -412,7 +408,7 @@ int sph_step(sph_handle *h, int nsteps, sph_step_info *info) {
         // getAcc #1, dt, statistics                                   F/isothermal_sim.jl:155-192
         rc = eval_internal(h, h->pos, h->vel, poly ? h->kent : nullptr, h->acc);
         if (rc) break;
-        cudaError_t e = sph_launch_dt(h, h->vel, h->acc);
+        cudaError_t e = sph_launch_dt(h);
         if (e == cudaSuccess) e = sph_launch_stats(h, log_dev + (size_t)s * 11);
         // predictor                                                   :197-200
         if (e == cudaSuccess) e = sph_launch_predict(h);
@@ -473,6 +469,7 @@ int sph_get_hydro(sph_handle *h, double *ahyd, double *rho, double *hsml, double
     if (!h->have_eval) return sph_fail(h, SPH_ERR_STATE, "sph_get_hydro: no force evaluation yet");
     SPH_CUDA(h, cudaSetDevice(h->p.device));
     const size_t N = (size_t)h->N;
+    SPH_CUDA(h, sph_launch_unpermute(h));
     int rc;
     if ((rc = d2h(h, ahyd, h->o_ahyd, 3 * N)) || (rc = d2h(h, rho, h->o_rho, N)) || (rc = d2h(h, hsml, h->o_h, N)) ||
         (rc = d2h(h, sum_vdw, h->o_sumvdw, N)) || (rc = d2h(h, mumax, h->o_mumax, N)) ||
@@ -486,6 +483,7 @@ int sph_get_grav(sph_handle *h, double *g, double *phi) {
     if (!h) return SPH_ERR_INVALID;
     if (!h->have_eval) return sph_fail(h, SPH_ERR_STATE, "sph_get_grav: no force evaluation yet");
     SPH_CUDA(h, cudaSetDevice(h->p.device));
+    SPH_CUDA(h, sph_launch_unpermute(h));
     int rc;
     if ((rc = d2h(h, g, h->o_g, 3 * (size_t)h->N)) || (rc = d2h(h, phi, h->o_phi, (size_t)h->N))) return rc;
     SPH_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -561,7 +559,8 @@ int sph_density_at(sph_handle *h, const double *pts, int64_t M, double *rho_out)
     if (M == 0) return SPH_OK;
     SPH_CUDA(h, cudaSetDevice(h->p.device));
     // search structure of the uploaded positions (keys, sort, tree); neighbour lists of an earlier
-    // evaluation no longer match it afterwards
+    // evaluation no longer match it afterwards (its per-particle results are un-permuted first)
+    if (h->have_eval) SPH_CUDA(h, sph_launch_unpermute(h));
     h->lists_valid = false;
     SPH_CUDA(h, sph_launch_domain_keys(h, h->pos));
     SPH_CUDA(h, sph_launch_permute(h, h->pos, h->vel, nullptr));
@@ -605,6 +604,10 @@ int sph_comm_init(sph_handle *h, int nranks, int rank, const void *id128) {
     h->nccl = comm;
     h->nranks = nranks;
     h->rank = rank;
+    {   // tiles of 128 walk targets are dealt round-robin: ceil(tiles / nranks) tiles per rank
+        const int64_t tiles = (h->N + 127) / 128;
+        h->walk_chunk = (tiles + nranks - 1) / nranks * 128;
+    }
     return SPH_OK;
 }
 

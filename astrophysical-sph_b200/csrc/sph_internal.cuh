@@ -130,6 +130,7 @@ struct sph_handle {
     double *in_pos = nullptr, *in_vel = nullptr, *in_kent = nullptr, *in_acc = nullptr;
     const double *last_acc = nullptr;  // acceleration array written by the last evaluation
     bool lists_valid = false;          // neighbour lists match the current sort
+    bool outputs_fresh = false;        // o_* arrays (other than o_h) hold the last evaluation's results
     bool hint_valid = false;           // o_h holds smoothing lengths of a completed evaluation (search radius hint)
     bool no_hint = false;              // SPH_B200_NO_HINT: always search from the guaranteed radius
     // per-evaluation outputs, orig order
@@ -147,10 +148,15 @@ struct sph_handle {
     double *cs_s = nullptr;     // sound speed (sorted)
     double *d2k = nullptr;
     int *nbr = nullptr;         // N x K
-    double *s_ahyd = nullptr;   // 3N, sorted: direct + scattered hydro acceleration
-    double *s_dkdt = nullptr, *s_sumvdw = nullptr, *s_mumax = nullptr;
-    double *s_g = nullptr;      // 3N sorted
-    double *s_phi = nullptr;
+    // one buffer [6][NS]: a_hyd x,y,z (direct + scattered), dK/dt sum, sum_vdw, mumax -> a single all-reduce in multi-GPU
+    // runs (only the owner of a target writes the last two, the other ranks contribute zeros)
+    double *s_red = nullptr;
+    double *s_ahyd = nullptr, *s_dkdt = nullptr, *s_sumvdw = nullptr, *s_mumax = nullptr;   // views into s_red
+    // walk results [rank][4][walk_chunk]: tiles of 128 targets are dealt round-robin to the ranks (load balance), each
+    // rank writes its tiles compactly -> a single in-place all-gather
+    double *walk_buf = nullptr;
+    double *walk_part = nullptr;   // [8 root children][4][walk_chunk] partial walk results of this rank
+    int64_t walk_chunk = 0;
     int *cnt = nullptr, *base = nullptr;  // per-particle node counts / offsets (N+1)
     SphTree tree;
     // device scalars: [0] l_domain bits, [1] n_nodes, [2] error flags, [3] dt bits, [4] visits
@@ -211,11 +217,12 @@ cudaError_t sph_launch_eos(sph_handle *h);
 cudaError_t sph_launch_force(sph_handle *h, int64_t t0, int64_t t1);
 
 // ---- gravity.cu ----------------------------------------------------------------------------------
-cudaError_t sph_launch_walk(sph_handle *h, int64_t t0, int64_t t1);
+cudaError_t sph_launch_walk(sph_handle *h);
 
 // ---- integrate.cu --------------------------------------------------------------------------------
 cudaError_t sph_launch_finish(sph_handle *h, double *acc_out);
-cudaError_t sph_launch_dt(sph_handle *h, const double *vel, const double *acc);
+cudaError_t sph_launch_dt(sph_handle *h);
+cudaError_t sph_launch_unpermute(sph_handle *h);
 cudaError_t sph_launch_stats(sph_handle *h, double *log_row_dev);
 cudaError_t sph_launch_set_time(sph_handle *h, double t);
 cudaError_t sph_launch_predict(sph_handle *h);
