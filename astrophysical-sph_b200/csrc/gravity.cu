@@ -213,6 +213,168 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 6) walk_kernel(int64_t N, int n
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Batched walk (opt-in: SPH_B200_WALK_BATCH=1).  Same decisions and the same per-lane arithmetic as walk_kernel above, but the
+// warp pops up to 32 cells per round: lane k fetches the 64-byte record of cell k (coalesced-ish: siblings
+// are contiguous) and parks it in shared memory; then every lane - one target each - runs over the parked
+// cells reading them with broadcast shared-memory loads.  The inner loop has no global loads, no stack
+// traffic and no votes; the lanes that must open cell k are collected afterwards with one vote per cell,
+// and the owners of opened cells push the children (exclusive scan for the stack slots).
+// The batch size adapts so that the shared-memory stack can never overflow (B <= (CAP - sp) / 7; B = 1 is
+// the depth-first walk whose depth is bounded by 7 * 21 + 8 entries).
+// ---------------------------------------------------------------------------------------------------
+constexpr int GB_WARPS = 4;
+constexpr int GB_CAP = 768;      // stack entries per warp
+
+struct GbWarp {
+    double4 recA[32];            // {rCOM, Mass | h_j}
+    double4 recV[32];            // {(2L)^2, radius, child info, range}
+    int2 ent[32];                // {cell id | leaf << 31, lane mask}
+    int2 stack[GB_CAP + 160];   // + the depth-first excursion of the B = 1 regime
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(GB_WARPS * 32, 4) walk_batch_kernel(int64_t N, int nranks, int rank, int64_t chunk,
+                                                                      const double4 *__restrict__ pos4, SphTree t,
+                                                                      double theta_sq, double th_lo, double th_hi, double m,
+                                                                      unsigned long long *__restrict__ scal,
+                                                                      double *__restrict__ part /* [8][4][chunk] */) {
+    extern __shared__ __align__(16) unsigned char gb_smem_raw[];
+    if (scal[SC_ERR] != 0ull) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    GbWarp &sm = reinterpret_cast<GbWarp *>(gb_smem_raw)[warp];
+    const double4 *__restrict__ W = t.nodeW;
+    const int64_t local = (int64_t)blockIdx.x * (GB_WARPS * 32) + threadIdx.x;
+    const int64_t s = ((int64_t)blockIdx.x * nranks + rank) * (GB_WARPS * 32) + threadIdx.x;
+    const bool active = s < N;
+    double px = 0, py = 0, pz = 0, hi = 1.0;
+    if (active) {
+        const double4 p = pos4[s];  // .w = h_i
+        px = p.x; py = p.y; pz = p.z; hi = p.w;
+    }
+    const double hi2 = hi * hi;
+    const double h2x = 2.0 * hi * (1.0 + 1e-9);      // clause 2 is certainly true when mindist > h2x
+    double gx = 0.0, gy = 0.0, gz = 0.0, ph = 0.0;
+    unsigned long long visits = 0;
+    const unsigned amask = __ballot_sync(0xffffffffu, active);
+    // the root is opened unconditionally (:246-249); its children are dealt to blockIdx.y (see walk_kernel)
+    const int rc = blockIdx.y;
+    const int2 R = unpack_i2(W[1].z);
+    if (rc >= (R.y & 0xff)) return;
+    int sp = 0;
+    if (amask) {
+        if (lane == 0) sm.stack[0] = make_int2((R.x + rc) | (int)((((unsigned)(R.y >> 8) >> rc) & 1u) << 31), (int)amask);
+        sp = 1;
+    }
+    __syncwarp();
+    while (sp > 0) {
+        // ---- pop a batch
+        int B = (GB_CAP - sp) / 7;
+        B = B < 1 ? 1 : (B > 32 ? 32 : B);
+        B = B < sp ? B : sp;
+        sp -= B;
+        int2 e = make_int2(0, 0);
+        double4 A = make_double4(0, 0, 0, 0), V = A;
+        if (lane < B) {
+            e = sm.stack[sp + lane];
+            const int64_t n = e.x & 0x7fffffff;
+            A = W[2 * n];
+            V = W[2 * n + 1];
+            sm.recA[lane] = A; sm.recV[lane] = V; sm.ent[lane] = e;
+        }
+        __syncwarp();
+        // ---- every lane (target) visits the parked cells
+        unsigned openbits = 0;
+#pragma unroll 2
+        for (int k = 0; k < B; ++k) {
+            const int2 ek = sm.ent[k];
+            if (!((((unsigned)ek.y) >> lane) & 1u)) continue;
+            const double4 Ak = sm.recA[k];
+            const double dx = px - Ak.x, dy = py - Ak.y, dz = pz - Ak.z;   // p_i - rCOM (:255)
+            const double d_sq = sph_d2_exact(dx, dy, dz);                   // (:256)
+            if (COUNT) ++visits;
+            if (ek.x < 0) {
+                // leaf = one particle j; A.w carries h_j, its mass is m; the target's own leaf is skipped (:293-294)
+                const double4 Vk = sm.recV[k];
+                if ((int64_t)unpack_i2(Vk.z).x != s) {
+                    const double h_ij = (hi + Ak.w) / 2;                    // (:259)
+                    double gP, pot;
+                    if (d_sq > 4.0 * (h_ij * h_ij)) {                       // q > 2: Newtonian (:19-20)
+                        const double rinv = fast_rsqrt(d_sq);
+                        gP = rinv * rinv * rinv;
+                        pot = -rinv;
+                    } else {
+                        grav_pair(d_sq, h_ij, gP, pot);
+                    }
+                    const double mg = m * gP;
+                    gx += mg * dx; gy += mg * dy; gz += mg * dz;            // (:263)
+                    ph += m * pot;                                          // (:264)
+                }
+            } else {
+                const double4 Vk = sm.recV[k];
+                // clause 1: s*s/d_sq < theta_sq                                             (:265)
+                bool accept;
+                if (Vk.x < d_sq * th_lo) accept = true;
+                else if (Vk.x > d_sq * th_hi) accept = false;
+                else accept = Vk.x / d_sq < theta_sq;
+                // clause 2: h_i*h_i / mind2 < 0.25, proven from d > radius + 2 h_i, else the reference's expression
+                if (accept) {
+                    const double w = Vk.y + h2x;
+                    if (!(d_sq > w * w)) {
+                        const int n = ek.x;
+                        const double4 Bb = t.nodeB[n];
+                        const double4 Cc = t.nodeC[n];
+                        const double ex = axis_dist(Bb.x, Bb.w, px), ey = axis_dist(Bb.y, Cc.x, py),
+                                     ez = axis_dist(Bb.z, Cc.y, pz);
+                        accept = quotient_less(hi2, sph_d2_exact(ex, ey, ez), 0.25);
+                    }
+                }
+                if (accept) {
+                    const double rinv = fast_rsqrt(d_sq);
+                    const double f = Ak.w * (rinv * rinv * rinv);           // Mass / d^3  (:266-268)
+                    gx += f * dx; gy += f * dy; gz += f * dz;
+                    ph -= Ak.w * rinv;                                      // -Mass / d   (:269)
+                } else {
+                    openbits |= 1u << k;
+                }
+            }
+        }
+        // ---- who opens what: lane k learns the lanes that must descend into its cell
+        unsigned mymask = 0;
+        for (int k = 0; k < B; ++k) {
+            const unsigned mk = __ballot_sync(0xffffffffu, (openbits >> k) & 1u);
+            if (lane == k) mymask = mk;
+        }
+        // ---- owners of opened cells push the children
+        const int2 ci = unpack_i2(V.z);                     // {first child, nch | leafmask << 8} of this lane's cell
+        const int nch = (lane < B && mymask) ? (ci.y & 0xff) : 0;
+        int off = nch;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, off, o);
+            if (lane >= o) off += a;
+        }
+        const int total = __shfl_sync(0xffffffffu, off, 31);
+        off -= nch;
+        for (int c = 0; c < nch; ++c)
+            sm.stack[sp + off + c] = make_int2((ci.x + c) | (int)((((unsigned)(ci.y >> 8) >> c) & 1u) << 31), (int)mymask);
+        sp += total;
+        __syncwarp();
+    }
+    if (active) {
+        double *out = part + (size_t)rc * 4 * chunk;
+        out[local] = gx; out[local + chunk] = gy; out[local + 2 * chunk] = gz;
+        out[local + 3 * chunk] = rc == 0 ? ph - (m * (7.0 / 5) / hi) : ph;        // (:303), once
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
+        if (lane == 0) atomicAdd(scal + SC_VISITS, visits);
+    }
+    (void)lt;
+}
+
 // sum of the per-root-child partial results in child order -> this rank's section of walk_buf
 __global__ void walk_reduce_kernel(int64_t n4 /* 4 * chunk */, const double *__restrict__ part, const double4 *__restrict__ W,
                                    const unsigned long long *__restrict__ scal, double *__restrict__ out) {
@@ -254,7 +416,25 @@ cudaError_t sph_launch_walk(sph_handle *h) {
     const dim3 grid((unsigned)blocks, 8);
     sph_note(1);
     static const bool count = getenv("SPH_B200_COUNT_VISITS") != nullptr;
-    if (count)
+    // the batched walk (walk_batch_kernel) measures the same as the depth-first walk; it stays opt-in
+    static const bool dfs = getenv("SPH_B200_WALK_BATCH") == nullptr;
+    if (!dfs) {
+        static bool attr_set = false;
+        const size_t smem = sizeof(GbWarp) * GB_WARPS;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(walk_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(walk_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        const double lo = th2 * (1.0 - 1e-15), hi = th2 * (1.0 + 1e-15);
+        if (count)
+            walk_batch_kernel<true><<<grid, GB_WARPS * 32, smem, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4,
+                                                                              h->tree, th2, lo, hi, h->p.m, h->scal, h->walk_part);
+        else
+            walk_batch_kernel<false><<<grid, GB_WARPS * 32, smem, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4,
+                                                                               h->tree, th2, lo, hi, h->p.m, h->scal, h->walk_part);
+    } else if (count)
         walk_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
                                                                  th2, h->p.m, h->scal, h->walk_part);
     else

@@ -6,19 +6,18 @@
 // (d2 = (dx*dx + dy*dy) + dz*dz, no FMA), ties are ordered by the caller's particle index, so the
 // emitted lists are bit-identical to the CPU path.
 //
-// One warp per target, ball collection + one sort:
-//   1. guaranteed radius R0: the K particles around the target in key order all lie within
-//      max_j d2(target, j), so the ball of that radius holds at least K particles;
-//   2. trial radius: (2 h_prev * 1.1)^2 from the previous force evaluation of the same particle when that
-//      is smaller than R0 (positions move by <= v dt/2 between evaluations, F/isothermal_sim.jl:197);
-//   3. depth-first walk of the octree: up to 8 children of a cell are tested by 8 lanes (point-to-box
-//      distance with an absolute slack covering the <= 1 ulp mismatch between the reference's
-//      classification centre and its stored bounds); cells holding <= 32 particles are scanned as
-//      contiguous ranges of the sorted array (coalesced), hits are appended to a shared-memory buffer
-//      with a ballot prefix.  A full buffer is compacted by a warp bitonic sort that keeps the K best and
-//      tightens the radius (only taken on a cold start, when the radius is the loose R0);
-//   4. if the trial ball held fewer than K particles the search is repeated with R0 (exactness never
-//      depends on the hint); finally one bitonic sort by (d2, particle id) and the first K are emitted.
+// Two kernels:
+//   knn_kernel       one warp per target.  Guaranteed radius R0: the K particles around the target in key order
+//                    all lie within max_j d2(target, j), so that ball holds at least K particles; the trial radius
+//                    is (1.1 * 2 h_prev)^2 from the previous evaluation when smaller.  Depth-first walk: up to 8
+//                    children of a cell are tested by 8 lanes (point-to-box distance with an absolute slack for
+//                    the <= 1 ulp mismatch between the reference's classification centre and its stored bounds);
+//                    cells holding <= 32 particles are scanned as contiguous ranges (coalesced), hits go to a
+//                    shared-memory buffer by ballot prefix; a full buffer is compacted by a bitonic sort that keeps
+//                    the K best and tightens the radius.  If the trial ball held < K particles the search restarts
+//                    from R0.  Used for the first evaluation (no hint), for arbitrary query points (density_plot)
+//                    and for the targets the second kernel hands over.
+//   knn_quad_kernel  four targets per warp once hints exist (see its header); exactness never depends on the hint.
 #include "sph_internal.cuh"
 
 #include <climits>
@@ -104,7 +103,6 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_kernel(int64_t N, int K
     const int64_t ntargets = list ? (int64_t)scal[SC_KNN_RETRY] : t1 - t0;
     for (int64_t it = (int64_t)blockIdx.x * KNN_WARPS + warp; it < ntargets; it += nwarps) {
         const int64_t s = list ? (int64_t)list[it] : t0 + it;
-        if (s < 0 || (SELF && s >= N)) { if (lane == 0) atomicMax(scal + SC_KNN_DBG, 201ull); continue; }
         double qx, qy, qz;
         if (SELF) {
             const double4 q = pos4[s];
@@ -270,285 +268,6 @@ __global__ void point_density_kernel(int64_t M, int K, const double *__restrict_
         s += w;
     }
     rho[i] = m * s;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Grouped search (used once a radius hint exists, i.e. from the second force evaluation on).
-//
-// One warp owns 8 key-adjacent targets; lane = (target t = lane & 7, quarter = lane >> 3).  Every target has
-// its own trial ball R_t = 1.1 * 2 h_prev and "core" ball 2 h_prev.  The warp walks the octree once for the
-// bounding box of the 8 balls, in key order, and merges the overlapping buckets (cells of <= 32 particles =
-// contiguous ranges of the sorted array) into runs; the runs are streamed through shared memory in chunks of
-// 32 (coalesced loads), and the four lanes of a target test one quarter of each chunk against the target's
-// ball (broadcast shared-memory reads), appending hits to the target's core or shell column.
-// A target whose ball held >= K particles owns its exact K nearest: core hits first, then the K - |core|
-// smallest shell hits (or, when particles moved inwards, the core minus its |core| - K largest) - a few
-// short min/max scans instead of a sort.  Lists are therefore emitted UNORDERED (the consumers only need the
-// set and r_K = max; sph_get_neighbors sorts rows on export), column-major so stores stay coalesced.
-// Targets whose ball held < K particles, overflowed a column, or whose box spans too many candidates are
-// queued for the warp-per-target kernel above, which restarts from the guaranteed radius: exactness never
-// depends on the hint.
-// ---------------------------------------------------------------------------------------------------
-constexpr int KG_WARPS = 4;
-constexpr int KG_T = 8;          // targets per warp
-constexpr int KG_CAPC = 64;      // core hits per target (expected: K)
-constexpr int KG_CAPS = 48;      // shell hits per target (expected: 0.331 K = 16.5 +- 4 for K = 50)
-constexpr int KG_RANGES = 128;
-constexpr int KG_MAXCAND = 2048;
-
-struct KgWarp {
-    double cd2[KG_CAPC][KG_T];
-    double sd2[KG_CAPS][KG_T];
-    int cid[KG_CAPC][KG_T];
-    int sid[KG_CAPS][KG_T];
-    double stage[2][3][32];
-    int2 ranges[KG_RANGES];
-    int2 stack[KNN_STACK];
-    int ccnt[KG_T], scnt[KG_T];
-};
-
-__global__ void __launch_bounds__(KG_WARPS * 32, 3) knn_group_kernel(int64_t N, int K, int64_t t0, int64_t t1,
-                                                                     const double4 *__restrict__ pos4,
-                                                                     const int *__restrict__ perm, SphTree t,
-                                                                     const double *__restrict__ hint_h, double hint_fac2,
-                                                                     unsigned long long *__restrict__ scal, int stats,
-                                                                     int *__restrict__ retry_list,
-                                                                     int *__restrict__ nbr, double *__restrict__ d2k) {
-    extern __shared__ __align__(16) unsigned char kg_smem_raw[];
-    if (scal[SC_ERR] != 0ull) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    KgWarp &sm = reinterpret_cast<KgWarp *>(kg_smem_raw)[warp];
-    const unsigned lt = (1u << lane) - 1u;
-    const int tl = lane & (KG_T - 1), sub = lane >> 3;
-    const double ldom = __longlong_as_double((long long)scal[SC_LDOM]);
-    const double eps = ldom * 1e-14;
-    const double INF = __longlong_as_double(0x7ff0000000000000LL);
-
-    const int64_t ngroups = (t1 - t0 + KG_T - 1) / KG_T;
-    for (int64_t grp = (int64_t)blockIdx.x * KG_WARPS + warp; grp < ngroups; grp += (int64_t)gridDim.x * KG_WARPS) {
-        const int64_t s = t0 + grp * KG_T + tl;
-        const bool active = s < t1;
-        double qx = 0, qy = 0, qz = 0, Rsq = -1.0, Csq = -1.0;
-        bool need_retry = false;
-        if (active) {
-            const double4 q = pos4[s];
-            qx = q.x; qy = q.y; qz = q.z;
-            const double hh = hint_h[perm[s]];
-            if (hh > 0.0 && hh < INF) { Csq = 4.0 * hh * hh; Rsq = Csq * hint_fac2; }
-            else need_retry = true;
-        }
-        if (lane < KG_T) { sm.ccnt[lane] = 0; sm.scnt[lane] = 0; }
-        // ---- bounding box of the 8 balls
-        const bool searching = active && !need_retry;
-        const double R = searching ? sqrt(Rsq) * (1.0 + 1e-12) + eps : 0.0;
-        double blo[3] = {searching ? qx - R : INF, searching ? qy - R : INF, searching ? qz - R : INF};
-        double bhi[3] = {searching ? qx + R : -INF, searching ? qy + R : -INF, searching ? qz + R : -INF};
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {   // lanes with equal (lane & 7) hold the same target
-                blo[a] = fmin(blo[a], __shfl_xor_sync(0xffffffffu, blo[a], o));
-                bhi[a] = fmax(bhi[a], __shfl_xor_sync(0xffffffffu, bhi[a], o));
-            }
-        }
-        // ---- list the buckets that overlap the box, in key order, merging contiguous ones into runs
-        int nr = 0;
-        bool overflow = false;
-        if (__any_sync(0xffffffffu, searching)) {
-            int cur_start = 0, cur_count = 0, tot_run = 0;
-            int sp = 1;
-            if (lane == 0) sm.stack[0] = make_int2(0, 0);
-            __syncwarp();
-            while (sp > 0) {
-                --sp;
-                // lane 0 reads the entry and broadcasts it: control flow below depends on it and must be warp-uniform
-                int2 top = make_int2(0, 0);
-                if (lane == 0) { const volatile int *e = (const volatile int *)&sm.stack[sp]; top.x = e[0]; top.y = e[1]; }
-                top.x = __shfl_sync(0xffffffffu, top.x, 0);
-                top.y = __shfl_sync(0xffffffffu, top.y, 0);
-                __syncwarp();
-                if (top.y > 0) {   // a bucket: particles [top.x, top.x + top.y)
-                    // boxes that span far too many particles (key-order jumps, sparse halo particles around a
-                    // dense core) are cheaper in the warp-per-target search: stop listing early
-                    tot_run += top.y;
-                    if (tot_run > KG_MAXCAND) { overflow = true; break; }
-                    if (cur_count > 0 && top.x == cur_start + cur_count) cur_count += top.y;
-                    else {
-                        if (cur_count > 0) {
-                            if (nr >= KG_RANGES) { overflow = true; break; }
-                            if (lane == 0) sm.ranges[nr] = make_int2(cur_start, cur_count);
-                            ++nr;
-                        }
-                        cur_start = top.x; cur_count = top.y;
-                    }
-                    continue;
-                }
-                if (top.x < 0 || (unsigned long long)top.x >= scal[SC_NNODES]) {
-                    if (lane == 0) atomicMax(scal + SC_KNN_DBG, 104ull);
-                    overflow = true;
-                    break;
-                }
-                const int2 I = t.nodeI[top.x];
-                const int nch = I.y & 0xff, first = I.x;
-                if (first < 0 || (unsigned long long)(first + nch) > scal[SC_NNODES] || nch > 8) {
-                    if (lane == 0) atomicMax(scal + SC_KNN_DBG, 105ull);
-                    overflow = true;
-                    break;
-                }
-                bool pass = false;
-                int cstart = 0, ccount = 0;
-                if (lane < nch) {
-                    const int c = first + lane;
-                    const double4 B = t.nodeB[c];
-                    const double4 C = t.nodeC[c];
-                    pass = B.x <= bhi[0] && B.w >= blo[0] && B.y <= bhi[1] && C.x >= blo[1] && B.z <= bhi[2] && C.y >= blo[2];
-                    cstart = t.nstart[c];
-                    ccount = t.ncount[c];
-                }
-                // push in reverse so that the lowest child (smallest keys) is popped first
-                const unsigned pm = __ballot_sync(0xffffffffu, pass);
-                if (sp + __popc(pm) > KNN_STACK) {   // cannot happen for depth <= 21; never write out of bounds
-                    if (lane == 0) atomicMax(scal + SC_KNN_DBG, 101ull);
-                    overflow = true;
-                    break;
-                }
-                if (pass) {
-                    const int pos = sp + __popc(pm) - 1 - __popc(pm & lt);
-                    sm.stack[pos] = ccount <= KNN_BUCKET ? make_int2(cstart, ccount) : make_int2(first + lane, 0);
-                }
-                sp += __popc(pm);
-                __syncwarp();
-            }
-            if (!overflow && cur_count > 0) {
-                if (nr >= KG_RANGES) overflow = true;
-                else {
-                    if (lane == 0) sm.ranges[nr] = make_int2(cur_start, cur_count);
-                    ++nr;
-                }
-            }
-        }
-        __syncwarp();
-        {   // candidate volume of this group; boxes that span far too many particles (key-order jumps, sparse halo
-            // particles around a dense core) are cheaper in the warp-per-target search
-            int tot = 0;
-            bool bad = false;
-            for (int r = lane; r < nr; r += 32) {
-                const int2 rg = sm.ranges[r];
-                tot += rg.y;
-                bad = bad || rg.x < 0 || rg.y <= 0 || (int64_t)rg.x + rg.y > N;
-            }
-            if (__any_sync(0xffffffffu, bad)) {
-                if (lane == 0) atomicMax(scal + SC_KNN_DBG, 102ull);
-                overflow = true;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-            if (tot > KG_MAXCAND) overflow = true;
-            if (stats && lane == 0) {
-                atomicAdd(scal + SC_KNN_CAND, (unsigned long long)tot);
-                atomicMax(scal + SC_KNN_MAXC, (unsigned long long)tot);
-                if (tot > KG_MAXCAND) atomicAdd(scal + SC_KNN_BIG, 1ull);
-            }
-        }
-        if (overflow) { need_retry = active; nr = 0; }
-        // ---- stream the candidates: the 4 lanes of a target share each chunk of 32
-        const double R2 = (searching && !overflow) ? Rsq : -1.0;
-        bool full = false;
-        int buf = 0;
-        for (int r = 0; r < nr; ++r) {
-            const int2 rg = sm.ranges[r];
-            for (int c0 = 0; c0 < rg.y; c0 += 32) {
-                const int nc = min(32, rg.y - c0);
-                double(*st)[32] = sm.stage[buf];
-                buf ^= 1;
-                if (lane < nc) {
-                    const double4 p = pos4[rg.x + c0 + lane];
-                    st[0][lane] = p.x; st[1][lane] = p.y; st[2][lane] = p.z;
-                }
-                __syncwarp();
-#pragma unroll 4
-                for (int k = sub; k < nc; k += 4) {
-                    const double d2 = sph_d2_exact(qx - st[0][k], qy - st[1][k], qz - st[2][k]);
-                    if (d2 <= R2) {
-                        if (d2 <= Csq) {
-                            const int slot = atomicAdd(&sm.ccnt[tl], 1);
-                            if (slot < KG_CAPC) { sm.cd2[slot][tl] = d2; sm.cid[slot][tl] = rg.x + c0 + k; }
-                            else full = true;
-                        } else {
-                            const int slot = atomicAdd(&sm.scnt[tl], 1);
-                            if (slot < KG_CAPS) { sm.sd2[slot][tl] = d2; sm.sid[slot][tl] = rg.x + c0 + k; }
-                            else full = true;
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        // any of the 4 lanes of a target saw an overflow?
-        full = full || __shfl_xor_sync(0xffffffffu, (int)full, 8);
-        full = full || __shfl_xor_sync(0xffffffffu, (int)full, 16);
-        const int c = min(sm.ccnt[tl], KG_CAPC), e = min(sm.scnt[tl], KG_CAPS);
-        if (searching && !overflow && (full || c + e < K)) need_retry = true;
-        // ---- selection by the first lane of each target: members = K smallest of core u shell by (d2, id)
-        int ncore = c < K ? c : K, nshell = K - ncore;
-        if (searching && !need_retry && sub == 0) {
-            if (c > K) {
-                // drop the c - K largest core hits: move them behind position K
-                for (int rdrop = 0; rdrop < c - K; ++rdrop) {
-                    const int last = c - 1 - rdrop;
-                    int bi = 0;
-                    double bd = sm.cd2[0][tl];
-                    int bid = sm.cid[0][tl];
-                    for (int i = 1; i <= last; ++i) {
-                        const double di = sm.cd2[i][tl];
-                        const int ii = sm.cid[i][tl];
-                        if (cand_less(bd, bid, di, ii, perm)) { bd = di; bid = ii; bi = i; }
-                    }
-                    sm.cd2[bi][tl] = sm.cd2[last][tl]; sm.cid[bi][tl] = sm.cid[last][tl];
-                    sm.cd2[last][tl] = bd; sm.cid[last][tl] = bid;
-                }
-            }
-            // take the nshell smallest shell hits to the front of the shell column
-            for (int rs = 0; rs < nshell; ++rs) {
-                int bi = rs;
-                double bd = sm.sd2[rs][tl];
-                int bid = sm.sid[rs][tl];
-                for (int i = rs + 1; i < e; ++i) {
-                    const double di = sm.sd2[i][tl];
-                    const int ii = sm.sid[i][tl];
-                    if (cand_less(di, ii, bd, bid, perm)) { bd = di; bid = ii; bi = i; }
-                }
-                sm.sd2[bi][tl] = sm.sd2[rs][tl]; sm.sid[bi][tl] = sm.sid[rs][tl];
-                sm.sd2[rs][tl] = bd; sm.sid[rs][tl] = bid;
-            }
-            // r_K^2 = largest member distance
-            double mx;
-            if (nshell > 0) mx = sm.sd2[nshell - 1][tl];
-            else {
-                mx = 0.0;
-                for (int i = 0; i < ncore; ++i) mx = fmax(mx, sm.cd2[i][tl]);
-            }
-            d2k[s] = mx;
-        }
-        __syncwarp();
-        // ---- emit (unordered): rows of 8 consecutive targets, 4 columns per store instruction
-        if (searching && !need_retry) {
-            for (int j = sub; j < K; j += 4)
-                nbr[s + (int64_t)j * N] = j < ncore ? sm.cid[j][tl] : sm.sid[j - ncore][tl];
-        }
-        // ---- queue the rest for the warp-per-target search
-        const unsigned rm = __ballot_sync(0xffffffffu, need_retry && sub == 0);
-        if (rm) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(scal + SC_KNN_RETRY, (unsigned long long)__popc(rm));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (need_retry && sub == 0) {
-                if (base + __popc(rm & lt) >= (unsigned long long)N) { atomicMax(scal + SC_KNN_DBG, 103ull); atomicMax(scal + SC_KNN_HITS, base); atomicMax(scal + SC_KNN_BIG, (unsigned long long)rm); }
-                else retry_list[base + __popc(rm & lt)] = (int)s;
-            }
-        }
-        __syncwarp();
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -820,7 +539,7 @@ cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1) {
     double fac2 = 1.1 * 1.1;
     static const double quad_fac = getenv("SPH_B200_KNN_FAC") ? atof(getenv("SPH_B200_KNN_FAC")) : 1.06;
     static const bool quad_off = getenv("SPH_B200_KNN_WARP") != nullptr;
-    if (hint && h->K <= 64 && !quad_off && getenv("SPH_B200_KNN_GROUP") == nullptr) {
+    if (hint && h->K <= 64 && !quad_off) {
         // 4 targets per warp for the hinted targets, then the warp-per-target search for whatever it queued
         sph_note(2);
         fac2 = quad_fac * quad_fac;
@@ -833,35 +552,6 @@ cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1) {
         // the guaranteed radius inside the kernel
         knn_kernel<128, true><<<148 * 5, KNN_WARPS * 32, 0, h->stream>>>(
             h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, 1.1 * 1.1, h->cnt, h->scal, h->nbr, h->d2k, nullptr);
-        return cudaGetLastError();
-    }
-    // the grouped search is opt-in (SPH_B200_KNN_GROUP=1): it is not yet faster than the warp-per-target search
-    static const bool warp_only = getenv("SPH_B200_KNN_GROUP") == nullptr;
-    if (hint && h->K <= KG_CAPC - 8 && !warp_only) {
-        // grouped search for the hinted targets, then the warp-per-target search for whatever it queued
-        static bool attr_set = false;
-        static const bool stats = getenv("SPH_B200_COUNT_VISITS") != nullptr;
-        const size_t smem = sizeof(KgWarp) * KG_WARPS;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(knn_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
-        sph_note(2);
-        const int64_t groups = (t1 - t0 + KG_T - 1) / KG_T;
-        int64_t blocks = (groups + KG_WARPS - 1) / KG_WARPS;
-        if (blocks > 148 * 3 * 8) blocks = 148 * 3 * 8;
-        knn_group_kernel<<<(int)blocks, KG_WARPS * 32, smem, h->stream>>>(
-            h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2, h->scal, (int)stats, h->cnt, h->nbr, h->d2k);
-        if (getenv("SPH_B200_TRACE")) {
-            cudaError_t e = cudaStreamSynchronize(h->stream);
-            unsigned long long sc[SC_COUNT];
-            cudaMemcpy(sc, h->scal, sizeof(sc), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[sph_b200 trace] group kernel done (%s): retry %llu cand %llu dbg %llu\n", cudaGetErrorString(e),
-                    sc[SC_KNN_RETRY], sc[SC_KNN_CAND], sc[SC_KNN_DBG]);
-        }
-        knn_kernel<128, true><<<148 * 5, KNN_WARPS * 32, 0, h->stream>>>(
-            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, nullptr, fac2, h->cnt, h->scal, h->nbr, h->d2k, nullptr);
         return cudaGetLastError();
     }
     sph_note(1);

@@ -94,7 +94,6 @@ int check_flags(sph_handle *h) {
                         h->stream) != cudaSuccess ||
         cudaStreamSynchronize(h->stream) != cudaSuccess)
         return sph_fail(h, SPH_ERR_CUDA, std::string("device error: ") + cudaGetErrorString(cudaGetLastError()));
-    if (h->h_scal[SC_KNN_DBG]) fprintf(stderr, "[sph_b200] KNN DEBUG CODE %llu base %llu rm %llx retry %llu\n", h->h_scal[SC_KNN_DBG], h->h_scal[SC_KNN_HITS], h->h_scal[SC_KNN_BIG], h->h_scal[SC_KNN_RETRY]);
     const unsigned long long f = h->h_scal[SC_STICKY] | h->h_scal[SC_ERR];
     if (f) {
         cudaMemsetAsync(h->scal + SC_STICKY, 0, sizeof(unsigned long long), h->stream);
@@ -537,9 +536,6 @@ int sph_get_timings(sph_handle *h, sph_timings *out) {
     SPH_CUDA(h, cudaMemcpy(h->h_scal, h->scal, sizeof(unsigned long long) * SC_COUNT, cudaMemcpyDeviceToHost));
     out->walk_visits = (double)h->h_scal[SC_VISITS];
     out->knn_retries = (double)h->h_scal[SC_KNN_RETRY];
-    if (getenv("SPH_B200_COUNT_VISITS"))
-        fprintf(stderr, "[sph_b200] knn tiles: candidates %llu, max/tile %llu, tiles over limit %llu, retries %llu\n",
-                h->h_scal[SC_KNN_CAND], h->h_scal[SC_KNN_MAXC], h->h_scal[SC_KNN_BIG], h->h_scal[SC_KNN_RETRY]);
     return SPH_OK;
 }
 

@@ -175,8 +175,7 @@ struct sph_handle {
 };
 
 // scal[0..SC_RESET) is cleared at the start of every force evaluation; SC_STICKY accumulates error flags
-enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_KNN_RETRY, SC_KNN_CAND, SC_KNN_BIG, SC_KNN_MAXC, SC_KNN_HITS, SC_KNN_DBG,
-       SC_RESET = 15, SC_STICKY = 15, SC_COUNT = 16 };
+enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_KNN_RETRY, SC_RESET = 15, SC_STICKY = 15, SC_COUNT = 16 };
 enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4 };
 
 int sph_fail(sph_handle *h, int code, const std::string &msg);
