@@ -88,7 +88,7 @@ __device__ __forceinline__ double pack_i2(int x, int y) {
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(GW_WARPS * 32, 6) walk_kernel(int64_t N, int nranks, int rank, int64_t chunk,
+__global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int nranks, int rank, int64_t chunk,
                                                                  const double4 *__restrict__ pos4, SphTree t,
                                                                  double theta_sq, double m,
                                                                  unsigned long long *__restrict__ scal,
@@ -134,12 +134,10 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 6) walk_kernel(int64_t N, int n
             if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)ERRF_STACK);
             break;
         }
-        double4 A_next = W[2 * (int64_t)first], V_next = W[2 * (int64_t)first + 1];
 #pragma unroll 1
         for (int c = 0; c < nch; ++c) {
             const int n = first + c;
-            const double4 A = A_next, V = V_next;   // A = {rCOM, Mass | h_j}, V = {(2L)^2, radius, child info, range}
-            if (c + 1 < nch) { A_next = W[2 * (int64_t)n + 2]; V_next = W[2 * (int64_t)n + 3]; }   // children are contiguous
+            const double4 A = W[2 * (int64_t)n], V = W[2 * (int64_t)n + 1];   // A = {rCOM, Mass | h_j}, V = {(2L)^2, radius, child info, range}
             const double dx = px - A.x, dy = py - A.y, dz = pz - A.z;   // p_i - rCOM (:255)
             const double d_sq = sph_d2_exact(dx, dy, dz);                // (:256)
             if (COUNT && mine) ++visits;
