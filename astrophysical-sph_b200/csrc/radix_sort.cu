@@ -6,7 +6,7 @@
 // NearestNeighbors.jl (F/isothermal_hydroKDTree.jl:128): one sort by 63-bit octant path key orders the
 // particles so that EVERY octree cell of every level is a contiguous range.
 //
-// Pass structure (8 bits per pass, tile = 256 threads x 16 keys):
+// Pass structure (8 bits per pass, tile = 256 threads x 4 keys):
 //   hist    per-tile digit histogram           -> ghist[digit][tile]
 //   scan    exclusive scan of ghist (digit-major, so the scan yields global start offsets)
 //   scatter stable in-tile ranking with __match_any_sync + per-warp digit counters, then scatter
@@ -18,7 +18,7 @@ namespace {
 constexpr int RS_BITS = 8;
 constexpr int RS_BINS = 1 << RS_BITS;
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;
+constexpr int RS_ITEMS = 4;     // 1024-key tiles: ~1000 blocks at N = 1e6 keep all SMs busy (16 items ran at 1.6 blocks per SM)
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 constexpr int RS_WARPS = RS_THREADS / 32;
 
