@@ -85,11 +85,12 @@ __global__ void __launch_bounds__(HB) eos_kernel(int64_t N, const double2 *__res
 
 // Pair loop of hydroCalculation / getAV / evolve_K!.  The target's own update is kept in registers and
 // stored once; the reaction on the neighbour (a_j += ct*gradW, dK_j += c2) is a double-precision RED to L2.
-__global__ void __launch_bounds__(HB) force_kernel(int64_t N, int64_t NS, int K, int64_t t0, int64_t t1,
+template <bool POLY>
+__global__ void __launch_bounds__(HB, 6) force_kernel(int64_t N, int64_t NS, int K, int64_t t0, int64_t t1,
                                                     const double4 *__restrict__ pos4, const double4 *__restrict__ vel4,
                                                     const double2 *__restrict__ hr, const double *__restrict__ prr,
                                                     const double *__restrict__ cs_s, const int *__restrict__ nbr,
-                                                    double m, double alpha, double beta, int poly,
+                                                    double m, double alpha, double beta,
                                                     const unsigned long long *__restrict__ scal,
                                                     double *__restrict__ ahyd, double *__restrict__ dkdt,
                                                     double *__restrict__ sumvdw, double *__restrict__ mumax) {
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(HB) force_kernel(int64_t N, int64_t NS, int K,
         const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;   // getTreeDiffs: f_i - f_j (:93)
         const double rr = sqrt(sph_d2_exact(dx, dy, dz));
         const double q = rr / hi;
-        const double dW = kernel_dWdr(ct4, hi, h2, q, rr, poly != 0);
+        const double dW = kernel_dWdr(ct4, hi, h2, q, rr, POLY);
         const double gx = dW * dx, gy = dW * dy, gz = dW * dz;
         const double h_avg = (hi + hrj.x) / 2;                               // getVectorTreeAvgs (:111)
         const double rho_avg = (rhoi + hrj.y) / 2;
@@ -128,14 +129,14 @@ __global__ void __launch_bounds__(HB) force_kernel(int64_t N, int64_t NS, int K,
         // (lists arrive unordered from the grouped search, so the self entry is recognised by its index)
         if (nj == s) continue;
         double ct;
-        if (!poly) ct = m * (prri + Pi / 2);                                 // iso :232
+        if (!POLY) ct = m * (prri + Pi / 2);                                 // iso :232
         else ct = m * ((prri + prr[nj]) + Pi) / 2;                           // poly :235
         const double fx = ct * gx, fy = ct * gy, fz = ct * gz;
         ax -= fx; ay -= fy; az -= fz;
         atomicAdd(&ahyd[nj], fx);
         atomicAdd(&ahyd[nj + NS], fy);
         atomicAdd(&ahyd[nj + 2 * NS], fz);
-        if (poly) {
+        if (POLY) {
             const double c2 = m * Pi * vdw / 2;                              // evolve_K! poly :305-311
             dk += c2;
             atomicAdd(&dkdt[nj], c2);
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(HB) force_kernel(int64_t N, int64_t NS, int K,
     atomicAdd(&ahyd[s], ax);
     atomicAdd(&ahyd[s + NS], ay);
     atomicAdd(&ahyd[s + 2 * NS], az);
-    if (poly) atomicAdd(&dkdt[s], dk);
+    if (POLY) atomicAdd(&dkdt[s], dk);
     sumvdw[s] = svdw;
     mumax[s] = mmax;
 }
@@ -175,8 +176,13 @@ cudaError_t sph_launch_force(sph_handle *h, int64_t t0, int64_t t1) {
     if (t1 <= t0) return cudaGetLastError();
     sph_note(1);
     const int64_t nt = t1 - t0;
-    force_kernel<<<(int)((nt + HB - 1) / HB), HB, 0, h->stream>>>(
-        N, h->NS, h->K, t0, t1, h->pos4, h->vel4, h->hr, h->prr, h->cs_s, h->nbr, h->p.m, h->p.alpha, h->p.beta,
-        h->p.eos == SPH_EOS_POLYTROPIC, h->scal, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax);
+    if (h->p.eos == SPH_EOS_POLYTROPIC)
+        force_kernel<true><<<(int)((nt + HB - 1) / HB), HB, 0, h->stream>>>(
+            N, h->NS, h->K, t0, t1, h->pos4, h->vel4, h->hr, h->prr, h->cs_s, h->nbr, h->p.m, h->p.alpha, h->p.beta,
+            h->scal, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax);
+    else
+        force_kernel<false><<<(int)((nt + HB - 1) / HB), HB, 0, h->stream>>>(
+            N, h->NS, h->K, t0, t1, h->pos4, h->vel4, h->hr, h->prr, h->cs_s, h->nbr, h->p.m, h->p.alpha, h->p.beta,
+            h->scal, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax);
     return cudaGetLastError();
 }
