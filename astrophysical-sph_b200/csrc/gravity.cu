@@ -22,22 +22,6 @@ namespace {
 constexpr int GW_WARPS = 4;
 constexpr int GW_STACK = 192;
 
-// 1/sqrt(x) and 1/x from the hardware seed (MUFU.RSQ64H / RCP64H, ~2^-22 relative) plus one Newton step each:
-// relative error <= 1e-13, five FP64 instructions instead of the IEEE sequences with their slow-path calls.
-// x must be a normal positive number (squared distances / smoothing lengths of distinct particles are).
-__device__ __forceinline__ double fast_rsqrt(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x * y, y, 1.0);          // 1 - x y^2
-    return fma(y * e, 0.5 + 0.375 * e, y);         // y (1 + e/2 + 3 e^2/8)
-}
-__device__ __forceinline__ double fast_rcp(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x, y, 1.0);
-    return fma(y * e, 1.0 + e, y);                 // y (1 + e + e^2)
-}
-
 // Kernels (F/gravOctree_Single.jl:5-29): grad(PHI)/r and PHI of the spline-softened potential, written in
 // q = r/h and 1/h (same polynomials; one reciprocal and one rsqrt instead of seven divisions)
 __device__ __forceinline__ void grav_pair(double d_sq, double h, double &gPHI, double &PHI) {

@@ -25,11 +25,12 @@ __device__ __forceinline__ double kernel_W(double ct, double q, bool poly) {
     return 0.0;
 }
 // (dW/dr)/r  (F/isothermal_hydroKDTree.jl:57-70)
-__device__ __forceinline__ double kernel_dWdr(double ct4, double h, double h2, double q, double r, bool poly) {
-    if (q <= 1.0) return ct4 * (9.0 / 4 * r / h2 - 3 / h);
+// hinv = 1/h, rinv = 1/r (approximations to 1e-13: the parity bar for the hydro force is 1e-9)
+__device__ __forceinline__ double kernel_dWdr(double ct4, double hinv, double q, double rinv, bool poly) {
+    if (q <= 1.0) return ct4 * hinv * (9.0 / 4 * q - 3);          // 9/4 r/h^2 - 3/h
     if (poly || q <= 2.0) {
         const double u = 2 - q;
-        return ct4 * (-3.0 / 4 * (u * u)) / r;
+        return ct4 * (-3.0 / 4 * (u * u)) * rinv;
     }
     return 0.0;
 }
@@ -45,12 +46,15 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int K, int64_t t
     const double4 pi = pos4[s];
     const double h = sqrt(d2k[s]) / 2;               // h = r[:, end] ./ 2   (:151)
     const double ct = 1 / (PI_D * (h * h * h));
+    const double hinv = 1 / h;
     double sum = 0.0;
     for (int j = 0; j < K; ++j) {
         const int nj = nbr[s + (int64_t)j * N];
         const double4 pj = pos4[nj];
-        const double r = sqrt(sph_d2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z));
-        sum += kernel_W(ct, r / h, poly != 0);       // rho_i = m * sum_j w_ij  (:175)
+        // q = r / h from one rsqrt seed + Newton step (1e-13 relative; the parity bar for rho is 1e-9)
+        const double d2 = sph_d2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+        const double q = d2 > 0.0 ? d2 * fast_rsqrt(d2) * hinv : 0.0;
+        sum += kernel_W(ct, q, poly != 0);           // rho_i = m * sum_j w_ij  (:175)
     }
     hr[s] = make_double2(h, m * sum);
 }
@@ -104,6 +108,7 @@ __global__ void __launch_bounds__(HB, 6) force_kernel(int64_t N, int64_t NS, int
     const double prri = prr[s], ci = cs_s[s];
     const double h2 = hi * hi;
     const double ct4 = 1 / (PI_D * (h2 * h2));
+    const double hinv = 1 / hi;
     double ax = 0.0, ay = 0.0, az = 0.0, svdw = 0.0, dk = 0.0;
     double mmax = -__longlong_as_double(0x7ff0000000000000LL);
     for (int j = 0; j < K; ++j) {
@@ -112,16 +117,17 @@ __global__ void __launch_bounds__(HB, 6) force_kernel(int64_t N, int64_t NS, int
         const double4 vj = vel4[nj];
         const double2 hrj = hr[nj];
         const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;   // getTreeDiffs: f_i - f_j (:93)
-        const double rr = sqrt(sph_d2_exact(dx, dy, dz));
-        const double q = rr / hi;
-        const double dW = kernel_dWdr(ct4, hi, h2, q, rr, POLY);
+        const double d2 = sph_d2_exact(dx, dy, dz);
+        const double rinv = d2 > 0.0 ? fast_rsqrt(d2) : 0.0;
+        const double q = d2 * rinv * hinv;
+        const double dW = kernel_dWdr(ct4, hinv, q, rinv, POLY);
         const double gx = dW * dx, gy = dW * dy, gz = dW * dz;
         const double h_avg = (hi + hrj.x) / 2;                               // getVectorTreeAvgs (:111)
         const double rho_avg = (rhoi + hrj.y) / 2;
         const double vx = vi.x - vj.x, vy = vi.y - vj.y, vz = vi.z - vj.z;
         const double vdr = (vx * dx + vy * dy) + vz * dz;                    // (:210)
-        const double mu = fmin(h_avg * vdr / (rr * rr + 0.01 * (h_avg * h_avg)), 0.0);   // (:211)
-        const double Pi = ((-alpha) * ci * mu + beta * (mu * mu)) / rho_avg;             // (:213)
+        const double mu = fmin(h_avg * vdr * fast_rcp(d2 + 0.01 * (h_avg * h_avg)), 0.0);   // (:211)
+        const double Pi = ((-alpha) * ci * mu + beta * (mu * mu)) * fast_rcp(rho_avg);       // (:213)
         const double vdw = (vx * gx + vy * gy) + vz * gz;
         svdw += vdw;
         mmax = fmax(mmax, mu);

@@ -286,9 +286,10 @@ __global__ void point_density_kernel(int64_t M, int K, const double *__restrict_
 // ---------------------------------------------------------------------------------------------------
 constexpr int KQ_T = 4;
 constexpr int KQ_CAP = 96;
-constexpr int KQ_WARPS = 6;
+constexpr int KQ_WARPS = 5;
+constexpr int KQ_BUCKET = 64;   // cells up to this size are scanned as ranges (fewer dependent node loads than 32)
 constexpr int KQ_BKS = 64;      // buckets gathered before a flush
-constexpr int KQ_CAND = 512;    // candidates gathered before a flush
+constexpr int KQ_CAND = 768;    // candidates gathered before a flush
 constexpr int KQ_MAXCAND = 3072; // quads whose box spans more candidates (key-order jumps) go to the per-target search
 
 struct KqWarp {
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
             for (;;) {
                 const bool last = sp == 0;
                 // ---- flush: expand the gathered buckets into a dense candidate list and test it in rounds of 32
-                if (nb > 0 && (last || nb + 8 > KQ_BKS || ncand + 8 * KNN_BUCKET > KQ_CAND)) {
+                if (nb > 0 && (last || nb + 8 > KQ_BKS || ncand + 8 * KQ_BUCKET > KQ_CAND)) {
                     tested += ncand;
                     if (tested > KQ_MAXCAND) {
                         // the box of these 4 targets straddles a jump of the key order: four small balls are cheaper
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
                     cstart = t.nstart[c];
                     ccount = t.ncount[c];
                 }
-                const bool is_bucket = ccount <= KNN_BUCKET;
+                const bool is_bucket = ccount <= KQ_BUCKET;
                 const unsigned bm = __ballot_sync(0xffffffffu, pass && is_bucket);
                 const unsigned im = __ballot_sync(0xffffffffu, pass && !is_bucket);
                 if (pass && !is_bucket) sm.stack[sp + __popc(im & lt)] = first + lane;
