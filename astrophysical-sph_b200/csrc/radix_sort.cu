@@ -6,11 +6,13 @@
 // NearestNeighbors.jl (F/isothermal_hydroKDTree.jl:128): one sort by 63-bit octant path key orders the
 // particles so that EVERY octree cell of every level is a contiguous range.
 //
-// Pass structure (8 bits per pass, tile = 256 threads x 4 keys):
-//   hist    per-tile digit histogram           -> ghist[digit][tile]
-//   scan    exclusive scan of ghist (digit-major, so the scan yields global start offsets)
-//   scatter stable in-tile ranking with __match_any_sync + per-warp digit counters, then scatter
-// HBM traffic per pass: 2 reads + 1 write of 12 B per element.
+// Default: one-sweep passes (8 bits per pass, tile = 256 threads x 8 keys): one histogram kernel for all passes, then
+// ONE kernel per pass that ranks its tile with __match_any_sync + per-warp digit counters, learns the digits of the
+// preceding tiles by decoupled look-back and scatters.  HBM traffic per pass: 1 read + 1 write of 12 B per element.
+// Classic three-kernel passes (hist / scan / scatter over ghist[digit][tile]) stay selectable with
+// SPH_B200_SORT_CLASSIC=1 and share the ranking code.
+#include <cstdlib>
+
 #include "sph_internal.cuh"
 
 namespace {
@@ -96,6 +98,135 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; ++it) {
+        const int64_t e = wbase + it * 32 + lane;
+        if (e < n) {
+            const unsigned dig = (unsigned)((key[it] >> shift) & (RS_BINS - 1));
+            const int dst = cnt[warp][dig] + rank[it];
+            keys_out[dst] = key[it];
+            vals_out[dst] = vals_in[e];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- one-sweep passes
+// One kernel per pass instead of five: the global digit counts of ALL passes come from one read of the keys
+// (os_hist_kernel), and inside a pass every tile obtains the number of equal digits in the tiles before it by a
+// decoupled look-back over per-tile status words {flag:2 | count:30} (tile ids are handed out by an atomic counter,
+// so a tile only ever waits for tiles whose blocks are already running).
+constexpr int OS_ITEMS = 8;
+constexpr int OS_TILE = RS_THREADS * OS_ITEMS;
+constexpr unsigned OS_AGG = 1u << 30, OS_INC = 2u << 30, OS_MASK = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(RS_THREADS) os_hist_kernel(const uint64_t *__restrict__ keys, int64_t n_cap,
+                                                              const unsigned long long *n_dev, int begin_bit, int npass,
+                                                              unsigned *__restrict__ ghist /* [npass][256] */) {
+    __shared__ unsigned hist[8][RS_BINS];
+    const int64_t n = eff_n(n_cap, n_dev);
+    for (int i = threadIdx.x; i < 8 * RS_BINS; i += RS_THREADS) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    for (int64_t e = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; e < n; e += (int64_t)gridDim.x * RS_THREADS) {
+        const uint64_t k = keys[e];
+        for (int p = 0; p < npass; ++p) atomicAdd(&hist[p][(unsigned)((k >> (begin_bit + p * RS_BITS)) & (RS_BINS - 1))], 1u);
+    }
+    __syncthreads();
+    for (int p = 0; p < npass; ++p) {
+        const unsigned c = hist[p][threadIdx.x];
+        if (c) atomicAdd(&ghist[p * RS_BINS + threadIdx.x], c);
+    }
+}
+
+// exclusive prefix over the 256 digits of every pass, in place
+__global__ void __launch_bounds__(RS_THREADS) os_prefix_kernel(unsigned *__restrict__ ghist, int npass) {
+    __shared__ unsigned sm[RS_BINS];
+    for (int p = 0; p < npass; ++p) {
+        const unsigned v = ghist[p * RS_BINS + threadIdx.x];
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < RS_BINS; o <<= 1) {
+            const unsigned t = threadIdx.x >= o ? sm[threadIdx.x - o] : 0u;
+            __syncthreads();
+            sm[threadIdx.x] += t;
+            __syncthreads();
+        }
+        ghist[p * RS_BINS + threadIdx.x] = sm[threadIdx.x] - v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) os_pass_kernel(const uint64_t *__restrict__ keys_in,
+                                                              const int *__restrict__ vals_in,
+                                                              uint64_t *__restrict__ keys_out, int *__restrict__ vals_out,
+                                                              int64_t n_cap, const unsigned long long *n_dev, int shift,
+                                                              const unsigned *__restrict__ gpref /* [256] */,
+                                                              volatile unsigned *status /* [ntiles][256] */,
+                                                              unsigned *tile_counter) {
+    __shared__ int cnt[RS_WARPS][RS_BINS];
+    __shared__ int s_tile;
+    const int64_t n = eff_n(n_cap, n_dev);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int tile = s_tile;
+    const int64_t wbase = (int64_t)tile * OS_TILE + (int64_t)warp * (32 * OS_ITEMS);
+    uint64_t key[OS_ITEMS];
+    int rank[OS_ITEMS];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int it = 0; it < OS_ITEMS; ++it) {
+        const int64_t e = wbase + it * 32 + lane;
+        const bool ok = e < n;
+        key[it] = ok ? keys_in[e] : 0ull;
+        const unsigned dig = ok ? (unsigned)((key[it] >> shift) & (RS_BINS - 1)) : (0x10000u + lane);
+        const unsigned grp = __match_any_sync(0xffffffffu, dig);
+        const int leader = __ffs(grp) - 1;
+        int pre = 0;
+        if (ok && lane == leader) {
+            pre = cnt[warp][dig];
+            cnt[warp][dig] = pre + __popc(grp);
+        }
+        pre = __shfl_sync(0xffffffffu, pre, leader);
+        rank[it] = pre + __popc(grp & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // thread d: tile total of digit d, look-back for the digits of the preceding tiles, per-warp start offsets
+        const int d = threadIdx.x;
+        unsigned total = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) total += (unsigned)cnt[w][d];
+        unsigned excl = 0;
+        if (tile == 0) {
+            status[d] = OS_INC | total;
+        } else {
+            status[(size_t)tile * RS_BINS + d] = OS_AGG | total;
+            // windows of 8 predecessors: the 8 loads are independent, so one L2 round trip covers 8 tiles
+            bool done = false;
+            for (int t = tile - 1; t >= 0 && !done; t -= 8) {
+                unsigned v[8];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) v[w] = t - w >= 0 ? status[(size_t)(t - w) * RS_BINS + d] : (2u << 30);
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    if (done) break;
+                    while ((v[w] >> 30) == 0u) { __nanosleep(20); v[w] = status[(size_t)(t - w) * RS_BINS + d]; }
+                    excl += v[w] & OS_MASK;
+                    done = (v[w] >> 30) == 2u;
+                }
+            }
+            status[(size_t)tile * RS_BINS + d] = OS_INC | (excl + total);
+        }
+        int run = (int)(gpref[d] + excl);
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const int c = cnt[w][d];
+            cnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < OS_ITEMS; ++it) {
         const int64_t e = wbase + it * 32 + lane;
         if (e < n) {
             const unsigned dig = (unsigned)((key[it] >> shift) & (RS_BINS - 1));
@@ -192,13 +323,20 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 }  // namespace
 
-size_t sph_sort_temp_bytes(int64_t n) {
+static size_t classic_temp_bytes(int64_t n) {
     const int64_t ntiles = cdiv(n, RS_TILE);
     const int64_t hist = (int64_t)RS_BINS * ntiles;
     const int64_t scan_tiles_hist = cdiv(hist, SC_TILE);
     const int64_t scan_tiles_n = cdiv(n + 1, SC_TILE);
     const int64_t st = scan_tiles_hist > scan_tiles_n ? scan_tiles_hist : scan_tiles_n;
     return align256((size_t)(hist + 1) * 4) * 2 + align256((size_t)(st + 2) * 4) + 1024;
+}
+static size_t onesweep_temp_bytes(int64_t n) {   // [8][256] counts, [8] tile counters, [8][ntiles][256] status words
+    return align256((size_t)(8 * RS_BINS + 8) * 4) + (size_t)8 * cdiv(n, OS_TILE) * RS_BINS * 4 + 1024;
+}
+size_t sph_sort_temp_bytes(int64_t n) {
+    const size_t a = classic_temp_bytes(n), b = onesweep_temp_bytes(n);
+    return a > b ? a : b;
 }
 
 cudaError_t sph_exclusive_scan(const int *in, int *out, int64_t n, void *temp, size_t temp_bytes, cudaStream_t st) {
@@ -217,6 +355,34 @@ cudaError_t sph_sort_pairs(uint64_t *keys_in, int *vals_in, uint64_t *keys_out, 
                            size_t temp_bytes, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     if (temp_bytes < sph_sort_temp_bytes(n)) return cudaErrorInvalidValue;
+    static const bool classic = getenv("SPH_B200_SORT_CLASSIC") != nullptr;
+    if (!classic) {
+        const int npass = (end_bit - begin_bit + RS_BITS - 1) / RS_BITS;
+        if (npass > 8) return cudaErrorInvalidValue;
+        const int ntiles = (int)cdiv(n, OS_TILE);
+        unsigned *ghist = (unsigned *)temp;
+        unsigned *counters = ghist + 8 * RS_BINS;
+        unsigned *status = (unsigned *)((char *)temp + align256((size_t)(8 * RS_BINS + 8) * 4));
+        cudaMemsetAsync(temp, 0, align256((size_t)(8 * RS_BINS + 8) * 4) + (size_t)npass * ntiles * RS_BINS * 4, st);
+        sph_note(2 + npass);
+        int hb = (int)cdiv(n, RS_THREADS * 16);
+        hb = hb < 1 ? 1 : (hb > 148 * 8 ? 148 * 8 : hb);
+        os_hist_kernel<<<hb, RS_THREADS, 0, st>>>(keys_in, n, n_dev, begin_bit, npass, ghist);
+        os_prefix_kernel<<<1, RS_THREADS, 0, st>>>(ghist, npass);
+        uint64_t *ka = keys_in, *kb = keys_out;
+        int *va = vals_in, *vb = vals_out;
+        for (int p = 0; p < npass; ++p) {
+            os_pass_kernel<<<ntiles, RS_THREADS, 0, st>>>(ka, va, kb, vb, n, n_dev, begin_bit + p * RS_BITS, ghist + p * RS_BINS,
+                                                          status + (size_t)p * ntiles * RS_BINS, counters + p);
+            uint64_t *tk = ka; ka = kb; kb = tk;
+            int *tv = va; va = vb; vb = tv;
+        }
+        if (ka != keys_out) {  // result currently in keys_in/vals_in
+            cudaMemcpyAsync(keys_out, ka, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(vals_out, va, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+        }
+        return cudaGetLastError();
+    }
     const int ntiles = (int)cdiv(n, RS_TILE);
     const int64_t hist = (int64_t)RS_BINS * ntiles;
     char *tp = (char *)temp;
