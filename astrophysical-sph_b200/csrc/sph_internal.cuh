@@ -120,6 +120,7 @@ struct SphTree {
     double4 *nodeW = nullptr;  // walk records, 2 x double4 per node: {com.xyz, mass | h_j}, {(2L)^2, radius, bits{first|slot, nch|leafmask<<8}, bits{nstart, ncount}}
     double2 *nodeD = nullptr;  // internal nodes: {(2 Length)^2, upper bound of the distance from rCOM to any point of the cell}
     int *nstart = nullptr, *ncount = nullptr, *ndepth = nullptr;
+    int *parent = nullptr, *arrive = nullptr;   // bottom-up COM sweep: parent id, number of finished children
     // build scratch
     int *old_start = nullptr, *old_depth = nullptr;  // node list in (start, depth) order
     uint64_t *dkey_in = nullptr, *dkey_out = nullptr;

@@ -11,6 +11,8 @@
 //   * cell geometry replays the reference's centre/bounds recurrence bit for bit (sph_cell_of);
 //   * masses / centres of mass are accumulated level by level from the deepest level up, children in
 //     octant order, as setCOMs! does in its reverse sweep (:183-211).
+#include <cstdlib>
+
 #include "sph_internal.cuh"
 
 namespace {
@@ -176,7 +178,56 @@ __global__ void __launch_bounds__(TB) node_build_kernel(const uint64_t *__restri
                 }
                 lo = nb;
             }
-            t.nodeI[k] = make_int2(bfs_of_old[o + 1], nch | (leafmask << 8));
+            const int fc = bfs_of_old[o + 1];
+            t.nodeI[k] = make_int2(fc, nch | (leafmask << 8));
+            for (int c = 0; c < nch; ++c) t.parent[fc + c] = (int)k;
+            if (k == 0) t.parent[0] = -1;
+        }
+    }
+}
+
+// Mass / rCOM / cell radius of one internal node from its (finished) children, children in octant order
+// (setCOMs!, F/gravOctree_Single.jl:197-208).  No FMA: the reference rounds each product.
+__device__ __forceinline__ void com_of_children(const SphTree &t, int k, int2 I) {
+    double tm = 0.0, wx = 0.0, wy = 0.0, wz = 0.0;
+    for (int c = 0; c < (I.y & 0xff); ++c) {
+        const double2 *ap = reinterpret_cast<const double2 *>(&t.nodeA[I.x + c]);   // L2 reads: written by other SMs in this launch
+        const double2 a0 = __ldcg(ap), a1 = __ldcg(ap + 1);
+        const double4 A = make_double4(a0.x, a0.y, a1.x, a1.y);
+        tm = __dadd_rn(tm, A.w);
+        wx = __dadd_rn(wx, __dmul_rn(A.w, A.x));
+        wy = __dadd_rn(wy, __dmul_rn(A.w, A.y));
+        wz = __dadd_rn(wz, __dmul_rn(A.w, A.z));
+    }
+    const double cx = wx / tm, cy = wy / tm, cz = wz / tm;
+    t.nodeA[k] = make_double4(cx, cy, cz, tm);
+    // radius of the cell about its COM (upper bound): lets the walk prove clause 2 of the acceptance test
+    // (h_i^2 / mindist^2 < 0.25) from d alone, since mindist >= d - radius
+    const double4 B = t.nodeB[k];
+    const double4 C = t.nodeC[k];
+    const double rx = fmax(cx - B.x, B.w - cx), ry = fmax(cy - B.y, C.x - cy), rz = fmax(cz - B.z, C.y - cz);
+    t.nodeD[k] = make_double2(C.z, sqrt(rx * rx + ry * ry + rz * rz) * (1.0 + 1e-12));
+}
+
+// Bottom-up sweep in ONE launch (replaces a launch per level): every leaf climbs towards the root; the thread that
+// completes a cell's last child (atomic arrival counter) computes the cell from its children and keeps climbing.
+// Results do not depend on the arrival order: a cell is always summed over all of its children in octant order.
+__global__ void __launch_bounds__(TB) com_bottomup_kernel(SphTree t, const unsigned long long *__restrict__ scal) {
+    if (scal[SC_ERR] != 0ull) return;
+    const int64_t M = (int64_t)scal[SC_NNODES];
+    for (int64_t k0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k0 < M; k0 += (int64_t)gridDim.x * blockDim.x) {
+        if (t.nodeI[k0].y != 0) continue;          // start at the leaves only
+        int k = (int)k0;
+        for (;;) {
+            const int p = t.parent[k];
+            if (p < 0) break;
+            const int2 I = t.nodeI[p];
+            __threadfence();                                   // my cell's data before my arrival
+            const int old = atomicAdd(&t.arrive[p], 1);
+            if (old != (I.y & 0xff) - 1) break;                // siblings still pending: their last one continues
+            __threadfence();
+            com_of_children(t, p, I);
+            k = p;
         }
     }
 }
@@ -243,7 +294,13 @@ cudaError_t sph_launch_tree(sph_handle *h) {
     node_inverse_kernel<<<grid_for(t.cap), TB, 0, st>>>(t.dval_out, t.old_depth, h->scal, t.bfs_of_old, t.level_start);
     node_build_kernel<<<grid_for(t.cap), TB, 0, st>>>(h->keys, N, h->cnt, h->base, t.dval_out, t.old_start,
                                                        t.old_depth, t.bfs_of_old, h->pos4, h->p.m, h->scal, t);
-    for (int lev = SPH_LEVELS - 1; lev >= 0; --lev)
-        com_level_kernel<<<grid_for(N / 4 + 1), TB, 0, st>>>(lev, t.level_start, t);
+    static const bool by_level = getenv("SPH_B200_COM_LEVELS") != nullptr;
+    if (by_level) {
+        for (int lev = SPH_LEVELS - 1; lev >= 0; --lev)
+            com_level_kernel<<<grid_for(N / 4 + 1), TB, 0, st>>>(lev, t.level_start, t);
+    } else {
+        cudaMemsetAsync(t.arrive, 0, sizeof(int) * (size_t)t.cap, st);
+        com_bottomup_kernel<<<grid_for(t.cap), TB, 0, st>>>(t, h->scal);
+    }
     return cudaGetLastError();
 }
