@@ -82,9 +82,10 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int n
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int4 *stack = s_stack[warp];
     const double4 *__restrict__ W = t.nodeW;
-    // block b of this rank owns tile b * nranks + rank (tiles of 128 key-adjacent targets, dealt round-robin)
+    // tiles of 128 key-adjacent targets are dealt round-robin in groups of SPH_WALK_DEAL consecutive tiles
     const int64_t local = (int64_t)blockIdx.x * (GW_WARPS * 32) + threadIdx.x;
-    const int64_t s = ((int64_t)blockIdx.x * nranks + rank) * (GW_WARPS * 32) + threadIdx.x;
+    const int64_t gtile = ((int64_t)(blockIdx.x / SPH_WALK_DEAL) * nranks + rank) * SPH_WALK_DEAL + blockIdx.x % SPH_WALK_DEAL;
+    const int64_t s = gtile * (GW_WARPS * 32) + threadIdx.x;
     const bool active = s < N;
     double px = 0, py = 0, pz = 0, hi = 1.0;
     if (active) {
@@ -228,7 +229,8 @@ __global__ void __launch_bounds__(GB_WARPS * 32, 4) walk_batch_kernel(int64_t N,
     GbWarp &sm = reinterpret_cast<GbWarp *>(gb_smem_raw)[warp];
     const double4 *__restrict__ W = t.nodeW;
     const int64_t local = (int64_t)blockIdx.x * (GB_WARPS * 32) + threadIdx.x;
-    const int64_t s = ((int64_t)blockIdx.x * nranks + rank) * (GB_WARPS * 32) + threadIdx.x;
+    const int64_t gtile = ((int64_t)(blockIdx.x / SPH_WALK_DEAL) * nranks + rank) * SPH_WALK_DEAL + blockIdx.x % SPH_WALK_DEAL;
+    const int64_t s = gtile * (GB_WARPS * 32) + threadIdx.x;
     const bool active = s < N;
     double px = 0, py = 0, pz = 0, hi = 1.0;
     if (active) {
@@ -391,7 +393,8 @@ cudaError_t sph_launch_walk(sph_handle *h) {
     sph_note(2);
     pack_nodes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->tree, h->pos4, h->scal);
     const int64_t tiles = (h->N + 127) / 128;
-    const int64_t blocks = (tiles - h->rank + h->nranks - 1) / h->nranks;   // tiles rank, rank + P, ...
+    const int64_t groups = (tiles + SPH_WALK_DEAL - 1) / SPH_WALK_DEAL;
+    const int64_t blocks = (groups - h->rank + h->nranks - 1) / h->nranks * SPH_WALK_DEAL;   // groups rank, rank + P, ...
     if (blocks <= 0) return cudaGetLastError();
     const double th2 = h->p.theta * h->p.theta;
     double *out = h->walk_buf + (size_t)h->rank * 4 * h->walk_chunk;

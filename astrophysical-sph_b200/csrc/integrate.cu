@@ -22,10 +22,12 @@ inline int grid_for(int64_t n) {
 // stat_dev layout
 enum { DV_T = 0, DV_DT = 1, DV_SUM = 2 /* 12 sums */, DV_L = 16 /* 3 sums */, DV_ROW = 20 /* 10 */ };
 
-// walk results of sorted slot s: tile = s / 128 went to rank tile % nranks as its (tile / nranks)-th tile
+// walk results of sorted slot s: tile = s / 128 belongs to group tile / SPH_WALK_DEAL, which went to rank
+// group % nranks as its (group / nranks)-th group
 __device__ __forceinline__ const double *walk_slot(const double *__restrict__ walk_buf, int nranks, int64_t wchunk, int64_t s) {
     const int64_t tile = s >> 7;
-    return walk_buf + (size_t)(tile % nranks) * 4 * wchunk + (tile / nranks) * 128 + (s & 127);
+    const int64_t group = tile / SPH_WALK_DEAL;
+    return walk_buf + (size_t)(group % nranks) * 4 * wchunk + ((group / nranks) * SPH_WALK_DEAL + tile % SPH_WALK_DEAL) * 128 + (s & 127);
 }
 
 // per evaluation: total acceleration and h in the caller's particle order (integrator, next search radius)

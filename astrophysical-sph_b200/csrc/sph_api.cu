@@ -24,6 +24,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, ncclConfig_t *) = nullptr;   // optional (NCCL >= 2.18)
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
@@ -47,6 +48,7 @@ NcclApi &nccl_api() {
         BIND(GetUniqueId) BIND(CommInitRank) BIND(CommDestroy) BIND(AllGather) BIND(AllReduce)
         BIND(GroupStart) BIND(GroupEnd) BIND(GetErrorString)
 #undef BIND
+        *(void **)(&api.CommSplit) = dlsym(api.lib, "ncclCommSplit");
         api.ok = true;
     });
     return api;
@@ -145,26 +147,48 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_KNN + 1], st));
     SPH_CUDA(h, sph_launch_density(h, t0, t1));
     TRACE("sph_launch_density done");
-    if (multi)  // every rank needs h and rho of all particles (neighbours of its targets, leaf softening)
+    if (multi) {  // every rank needs h and rho of all particles (neighbours of its targets, leaf softening)
+        SPH_CUDA(h, cudaEventRecord(h->cev[0], st));
         SPH_NCCL(h, nc.AllGather(h->hr + h->rank * chunk, h->hr, (size_t)chunk * 2, ncclDouble, comm, st));
+        SPH_CUDA(h, cudaEventRecord(h->cev[1], st));
+    }
     SPH_CUDA(h, sph_launch_eos(h));
     TRACE("sph_launch_eos done");
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_DENSITY + 1], st));
-    SPH_CUDA(h, sph_launch_force(h, t0, t1));
+    // ---- force (stream2 when overlapping) || walk (main stream): both depend only on the density/EOS results
+    const bool ov = h->overlap && (!multi || h->nccl2 != nullptr);
+    cudaStream_t fs = ov ? h->stream2 : st;
+    if (ov) {
+        SPH_CUDA(h, cudaEventRecord(h->ev_fork, st));
+        SPH_CUDA(h, cudaStreamWaitEvent(fs, h->ev_fork, 0));
+    }
+    SPH_CUDA(h, cudaEventRecord(h->fev[0], fs));
+    h->stream = fs;                       // the launch helpers enqueue on h->stream
+    cudaError_t fe = sph_launch_force(h, t0, t1);
+    h->stream = st;
+    SPH_CUDA(h, fe);
     TRACE("sph_launch_force done");
     if (multi) {
         // reactions a_j += ct*gradW land on particles of other ranks: sum the partial accelerations
         // (also carries sum_vdw and mumax of the owned targets: the other ranks hold zeros there)
-        SPH_NCCL(h, nc.AllReduce(h->s_red, h->s_red, (size_t)h->NS * 6, ncclDouble, ncclSum, comm, st));
+        SPH_CUDA(h, cudaEventRecord(h->cev[2], fs));
+        SPH_NCCL(h, nc.AllReduce(h->s_red, h->s_red, (size_t)h->NS * 6, ncclDouble, ncclSum,
+                                 ov ? (ncclComm_t)h->nccl2 : comm, fs));
+        SPH_CUDA(h, cudaEventRecord(h->cev[3], fs));
     }
+    SPH_CUDA(h, cudaEventRecord(h->fev[1], fs));
+    if (ov) SPH_CUDA(h, cudaEventRecord(h->ev_join, fs));
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_FORCE + 1], st));
     SPH_CUDA(h, sph_launch_walk(h));
     TRACE("sph_launch_walk done");
     if (multi) {
+        SPH_CUDA(h, cudaEventRecord(h->cev[4], st));
         SPH_NCCL(h, nc.AllGather(h->walk_buf + (size_t)h->rank * 4 * h->walk_chunk, h->walk_buf, (size_t)4 * h->walk_chunk,
                                  ncclDouble, comm, st));
+        SPH_CUDA(h, cudaEventRecord(h->cev[5], st));
     }
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_GRAV + 1], st));
+    if (ov) SPH_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
     SPH_CUDA(h, sph_launch_finish(h, acc_out));
     TRACE("sph_launch_finish done");
     sph_note(1);
@@ -254,13 +278,13 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(dalloc(&h->cs_s, NS)); CK(dalloc(&h->d2k, NS)); CK(dalloc(&h->nbr, N * K));
     CK(dalloc(&h->s_red, 6 * NS));
     h->s_ahyd = h->s_red; h->s_dkdt = h->s_red + 3 * NS; h->s_sumvdw = h->s_red + 4 * NS; h->s_mumax = h->s_red + 5 * NS;
-    h->walk_chunk = (int64_t)((N + 127) / 128) * 128;   // nranks = 1 until sph_comm_init
-    CK(dalloc(&h->walk_buf, 4 * ((size_t)h->walk_chunk + 128 * SPH_MAX_RANKS)));
+    h->walk_chunk = (int64_t)(((N + 127) / 128 + SPH_WALK_DEAL - 1) / SPH_WALK_DEAL) * SPH_WALK_DEAL * 128;   // nranks = 1 until sph_comm_init
+    CK(dalloc(&h->walk_buf, 4 * ((size_t)h->walk_chunk + 128 * SPH_WALK_DEAL * SPH_MAX_RANKS)));
     CK(dalloc(&h->walk_part, 8 * 4 * (size_t)h->walk_chunk));
     CK(dalloc(&h->cnt, N + 1)); CK(dalloc(&h->base, N + 2));
     CK(cudaMemset(h->hr, 0, NS * sizeof(double2)));
     CK(cudaMemset(h->s_red, 0, 6 * NS * 8));
-    CK(cudaMemset(h->walk_buf, 0, 4 * ((size_t)h->walk_chunk + 128 * SPH_MAX_RANKS) * 8));
+    CK(cudaMemset(h->walk_buf, 0, 4 * ((size_t)h->walk_chunk + 128 * SPH_WALK_DEAL * SPH_MAX_RANKS) * 8));
     {
         SphTree &t = h->tree;
         double factor = 3.0;
@@ -284,6 +308,12 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(cudaMallocHost((void **)&h->h_stat, 32 * sizeof(double)));
     CK(dalloc(&h->red_partial, (size_t)592 * 12));
     for (int i = 0; i <= PH_COUNT; ++i) CK(cudaEventCreate(&h->ev[i]));
+    for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&h->cev[i]));
+    CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreate(&h->fev[0])); CK(cudaEventCreate(&h->fev[1]));
+    h->overlap = getenv("SPH_B200_NO_OVERLAP") == nullptr;
     CK(cudaDeviceSynchronize());
 #undef CK
     *out = h;
@@ -294,6 +324,7 @@ int sph_destroy(sph_handle *h) {
     if (!h) return SPH_OK;
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->nccl2 && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t)h->nccl2);
     if (h->nccl && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t)h->nccl);
     void *ptrs[] = {h->pos, h->vel, h->kent, h->acc, h->pos_half, h->vel_half, h->in_pos, h->in_vel, h->in_kent,
                     h->in_acc, h->o_rho, h->o_h, h->o_phi, h->o_sumvdw, h->o_mumax, h->o_cs, h->o_dkdt, h->o_ahyd,
@@ -309,6 +340,13 @@ int sph_destroy(sph_handle *h) {
     if (h->h_stat) cudaFreeHost(h->h_stat);
     for (int i = 0; i <= PH_COUNT; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 6; ++i)
+        if (h->cev[i]) cudaEventDestroy(h->cev[i]);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (int i = 0; i < 2; ++i)
+        if (h->fev[i]) cudaEventDestroy(h->fev[i]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SPH_OK;
@@ -529,7 +567,13 @@ int sph_get_timings(sph_handle *h, sph_timings *out) {
     float ms[PH_COUNT];
     for (int i = 0; i < PH_COUNT; ++i) SPH_CUDA(h, cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
     out->sort_ms = ms[PH_SORT]; out->tree_ms = ms[PH_TREE]; out->knn_ms = ms[PH_KNN];
-    out->density_ms = ms[PH_DENSITY]; out->force_ms = ms[PH_FORCE]; out->gravity_ms = ms[PH_GRAV];
+    out->density_ms = ms[PH_DENSITY];
+    {   // the force phase is measured on the stream it ran on (it overlaps the walk)
+        float f = 0.f;
+        SPH_CUDA(h, cudaEventElapsedTime(&f, h->fev[0], h->fev[1]));
+        out->force_ms = f;
+    }
+    out->gravity_ms = ms[PH_GRAV];
     out->finish_ms = ms[PH_FINISH];
     float tot;
     SPH_CUDA(h, cudaEventElapsedTime(&tot, h->ev[0], h->ev[PH_COUNT]));
@@ -537,6 +581,13 @@ int sph_get_timings(sph_handle *h, sph_timings *out) {
     SPH_CUDA(h, cudaMemcpy(h->h_scal, h->scal, sizeof(unsigned long long) * SC_COUNT, cudaMemcpyDeviceToHost));
     out->walk_visits = (double)h->h_scal[SC_VISITS];
     out->knn_retries = (double)h->h_scal[SC_KNN_RETRY];
+    out->comm_ms = 0.0;
+    if (h->nranks > 1)
+        for (int i = 0; i < 3; ++i) {
+            float c = 0.f;
+            SPH_CUDA(h, cudaEventElapsedTime(&c, h->cev[2 * i], h->cev[2 * i + 1]));
+            out->comm_ms += c;
+        }
     return SPH_OK;
 }
 
@@ -601,9 +652,16 @@ int sph_comm_init(sph_handle *h, int nranks, int rank, const void *id128) {
     h->nccl = comm;
     h->nranks = nranks;
     h->rank = rank;
+    // second communicator for the stream that overlaps the force all-reduce with the walk; without ncclCommSplit the
+    // two phases simply stay on one stream
+    if (h->overlap && nc.CommSplit) {
+        ncclComm_t c2 = nullptr;
+        if (nc.CommSplit(comm, 0, rank, &c2, nullptr) == ncclSuccess) h->nccl2 = c2;
+    }
     {   // tiles of 128 walk targets are dealt round-robin: ceil(tiles / nranks) tiles per rank
         const int64_t tiles = (h->N + 127) / 128;
-        h->walk_chunk = (tiles + nranks - 1) / nranks * 128;
+        const int64_t groups = (tiles + SPH_WALK_DEAL - 1) / SPH_WALK_DEAL;
+        h->walk_chunk = (groups + nranks - 1) / nranks * SPH_WALK_DEAL * 128;
     }
     return SPH_OK;
 }

@@ -18,6 +18,8 @@
 
 #define SPH_LEVELS 21           // octant levels held by one 63-bit key
 #define SPH_MAX_RANKS 16
+#define SPH_WALK_DEAL 16         // walk tiles (128 targets) are dealt to the ranks in groups of 16 consecutive tiles:
+                                 // round-robin balances the load, consecutive tiles keep the tree nodes hot in L2
 
 #define HD __host__ __device__ __forceinline__
 
@@ -184,6 +186,13 @@ struct sph_handle {
     double *red_partial = nullptr;         // per-block partial sums of the statistics kernels
     // timing
     cudaEvent_t ev[PH_COUNT + 1]{};
+    cudaEvent_t cev[6]{};   // begin/end of the three collectives
+    // the force kernel (+ its all-reduce) runs on a second stream, concurrently with the tree walk: both only need
+    // the density/EOS results, and the latency-bound force kernel fills the issue slots the walk's tail leaves idle
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, fev[2]{};
+    void *nccl2 = nullptr;  // communicator of stream2 (NCCL calls of one communicator must not run concurrently)
+    bool overlap = true;
     bool ev_valid = false;
     // multi-GPU
     int nranks = 1, rank = 0;

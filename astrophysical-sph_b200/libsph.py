@@ -47,7 +47,7 @@ class SphStepInfo(C.Structure):
 
 class SphTimings(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("sort_ms", "tree_ms", "knn_ms", "density_ms", "force_ms", "gravity_ms",
-                                          "finish_ms", "total_ms", "walk_visits", "knn_retries")]
+                                          "finish_ms", "total_ms", "walk_visits", "knn_retries", "comm_ms")]
 
 
 class SphError(RuntimeError):

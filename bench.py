@@ -266,6 +266,7 @@ def run_b200(args, rank, world, local_rank):
                            "frac": round(ALG_BYTES_STEP * value / 1e9 / peak, 5)},
         "phases_last_eval": phases,
         "knn_retries": tim.get("knn_retries"),
+        "comm_ms_last_eval": tim.get("comm_ms"),
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -82,6 +82,7 @@ typedef struct sph_timings {
     double total_ms;
     double walk_visits;  /* sum over targets of node visits in the last walk (0 unless SPH_B200_COUNT_VISITS) */
     double knn_retries;  /* targets whose hinted search radius held < Kh particles and was repeated           */
+    double comm_ms;      /* of the above: time inside the three NCCL collectives (0 on a single GPU)         */
 } sph_timings;
 
 typedef struct sph_handle sph_handle;
