@@ -346,3 +346,17 @@ def test_run_simulation_writes_reference_files(sph, oracle, tmp_path):
     stats, _ = S.open_or_create_stats_mmap(os.path.join(root, "snapshots", "gaussian_sphere", "stats"))
     np.testing.assert_allclose(np.array(stats[:3, :5]), oo["stats"][:, :5], rtol=1e-9)
     assert not np.any(np.array(stats[3:10]))
+
+
+@pytest.mark.parametrize("env", ["SPH_B200_SORT_CLASSIC", "SPH_B200_COM_LEVELS", "SPH_B200_WALK_BATCH", "SPH_B200_NO_OVERLAP",
+                                 "SPH_B200_KNN_WARP", "SPH_B200_NO_HINT"])
+def test_alternative_paths_agree(sph, env):
+    """Every switchable kernel variant (classic sort passes, level-wise COM sweep, batched walk, serial force/walk,
+    warp-per-target search, unhinted search) passes the same two-step parity check against the oracle."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "alt_paths_check.py")], capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, **{env: "1"}))
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
