@@ -81,6 +81,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_steps(pos, vel, c, nsteps, nthreads):
     """nsteps loop iterations on the oracle (all phases, same code path the parity tests check against)."""
     from oracle import oracle as O
@@ -94,9 +102,7 @@ def cpu_reference_steps(pos, vel, c, nsteps, nthreads):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from oracle import oracle as O
-
-    nt = O.max_threads()
+    nt = host_threads()
     total = args.steps + args.warmup
     # bounded sample: the same IC family at a particle count that keeps the whole run within a few minutes
     n = args.n if total <= 8 else max(100_000, int(args.n * 8 / total) // 1000 * 1000)
@@ -231,9 +237,7 @@ def run_b200(args, rank, world, local_rank):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O
-
-        nt = O.max_threads()
+        nt = host_threads()
         dtc = cpu_reference_steps(pos, vel, c, 1, nt)
         cpu = {"value": n / dtc, "unit": "particle-steps/s", "cores": nt, "kind": "port",
                "sample": f"1 full step of the same N={n} workload on the oracle (C++ restatement of the Julia path, "
