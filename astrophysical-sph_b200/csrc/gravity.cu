@@ -21,6 +21,12 @@ namespace {
 
 constexpr int GW_WARPS = 4;
 constexpr int GW_STACK = 192;
+constexpr int GW_REC = SPH_WALK_REC;   // double4 per walk record: {rCOM, Mass | h_j}, {(2L)^2, radius, child info, range}, {lo.xyz, hi.x}, {hi.y, hi.z, ..}
+
+// coefficients of the softened kernels below, read as constant-bank operands (as literals each one costs two
+// uniform-register moves in front of the FP64 instruction that uses it)
+__constant__ double c_gk[13] = {4.0 / 3, 6.0 / 5, 1.0 / 2, 2.0 / 3, 3.0 / 10, 1.0 / 10, 7.0 / 5,
+                                8.0 / 3, 1.0 / 6, 1.0 / 15, 1.0 / 30, 8.0 / 5, 3.0};
 
 // Kernels (F/gravOctree_Single.jl:5-29): grad(PHI)/r and PHI of the spline-softened potential, written in
 // q = r/h and 1/h (same polynomials; one reciprocal and one rsqrt instead of seven divisions)
@@ -37,12 +43,12 @@ __device__ __forceinline__ void grav_pair(double d_sq, double h, double &gPHI, d
     const double q2 = q * q, q3 = q2 * q;
     const double hinv3 = hinv * hinv * hinv;
     if (q <= 1.0) {
-        gPHI = hinv3 * ((4.0 / 3 - 6.0 / 5 * q2) + 1.0 / 2 * q3);                                   // (:10)
-        PHI = hinv * (((2.0 / 3 * q2 - 3.0 / 10 * (q2 * q2)) + 1.0 / 10 * (q2 * q3)) - 7.0 / 5);     // (:11)
+        gPHI = hinv3 * ((c_gk[0] - c_gk[1] * q2) + c_gk[2] * q3);                                    // (:10)
+        PHI = hinv * (((c_gk[3] * q2 - c_gk[4] * (q2 * q2)) + c_gk[5] * (q2 * q3)) - c_gk[6]);       // (:11)
     } else {
         const double qi = rinv * h;  // 1/q
-        gPHI = hinv3 * ((((8.0 / 3 - 3 * q) + 6.0 / 5 * q2) - 1.0 / 6 * q3) - 1.0 / 15 * (qi * qi * qi));              // (:14)
-        PHI = hinv * (((((4.0 / 3 * q2 - q3) + 3.0 / 10 * (q2 * q2)) - 1.0 / 30 * (q2 * q3)) - 8.0 / 5) + 1.0 / 15 * qi);   // (:15)
+        gPHI = hinv3 * ((((c_gk[7] - c_gk[12] * q) + c_gk[1] * q2) - c_gk[8] * q3) - c_gk[9] * (qi * qi * qi));              // (:14)
+        PHI = hinv * (((((c_gk[0] * q2 - q3) + c_gk[4] * (q2 * q2)) - c_gk[10] * (q2 * q3)) - c_gk[11]) + c_gk[9] * qi);   // (:15)
     }
 }
 
@@ -52,6 +58,8 @@ __device__ __forceinline__ bool quotient_less(double a, double b, double c) {
     const double t = c * b;
     if (a < t * (1.0 - 1e-15)) return true;
     if (a > t * (1.0 + 1e-15)) return false;
+    asm volatile("");   // keeps the IEEE division inside the band: the compiler otherwise if-converts it and every
+                        // lane that fails the first comparison pays for a division
     return a / b < c;
 }
 
@@ -62,6 +70,13 @@ __device__ __forceinline__ double axis_dist(double lo, double hi, double p) {
     const double mx = a > b ? a : b;
     return mx > 0.0 ? mx : 0.0;
 }
+// the same value from the sign bits (integer pipe instead of two FP64 compares): a > 0 excludes b > 0, and a zero
+// of either sign yields 0 like the maximum does
+__device__ __forceinline__ double axis_dist_bits(double lo, double hi, double p) {
+    const double a = lo - p, b = p - hi;
+    const double bz = __double2hiint(b) >= 0 ? b : 0.0;
+    return __double2hiint(a) >= 0 ? a : bz;
+}
 
 __device__ __forceinline__ int2 unpack_i2(double v) {
     const long long b = __double_as_longlong(v);
@@ -69,6 +84,21 @@ __device__ __forceinline__ int2 unpack_i2(double v) {
 }
 __device__ __forceinline__ double pack_i2(int x, int y) {
     return __longlong_as_double((long long)(unsigned)x | ((long long)y << 32));
+}
+
+// Root child handled by block row y of a tile: row 0 takes the child that CONTAINS the tile (its walk is by far the
+// longest: the whole near field), rows 1.. the others in cyclic order.  The hardware starts blocks in grid order, so
+// every long work item begins before any short one and the short ones fill the tail.
+__device__ __forceinline__ int walk_root_child(const double4 *__restrict__ W, int2 R, int64_t first_slot, int y) {
+    const int nch = R.y & 0xff;
+    if (y >= nch) return -1;
+    int near = 0;
+    for (int c = 0; c < nch; ++c) {
+        const int2 rg = unpack_i2(W[GW_REC * (int64_t)(R.x + c) + 1].w);    // {nstart, ncount}
+        if (first_slot >= rg.x && first_slot < (int64_t)rg.x + rg.y) near = c;
+    }
+    const int rc = near + y;
+    return rc >= nch ? rc - nch : rc;
 }
 
 template <bool COUNT>
@@ -102,9 +132,9 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int n
     // the walk starts by opening the root: the root itself is never tested (:246-249).  The root's children are
     // dealt to blockIdx.y: 8x more, 8x shorter work items (wave quantisation matters when a rank owns ~1 wave of
     // tiles); the partial sums are added in child order by walk_reduce_kernel, so results stay deterministic.
-    const int rc = blockIdx.y;
     const int2 R = unpack_i2(W[1].z);
-    if (rc >= (R.y & 0xff)) return;
+    const int rc = walk_root_child(W, R, gtile * (GW_WARPS * 32), blockIdx.y);
+    if (rc < 0) return;
     if (amask) {
         if (lane == 0) stack[0] = make_int4(R.x + rc, 1 | ((((R.y >> 8) >> rc) & 1) << 8), (int)amask, 0);
         sp = 1;
@@ -122,7 +152,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int n
 #pragma unroll 1
         for (int c = 0; c < nch; ++c) {
             const int n = first + c;
-            const double4 A = W[2 * (int64_t)n], V = W[2 * (int64_t)n + 1];   // A = {rCOM, Mass | h_j}, V = {(2L)^2, radius, child info, range}
+            const double4 A = W[GW_REC * (int64_t)n], V = W[GW_REC * (int64_t)n + 1];   // A = {rCOM, Mass | h_j}, V = {(2L)^2, radius, child info, range}
             const double dx = px - A.x, dy = py - A.y, dz = pz - A.z;   // p_i - rCOM (:255)
             const double d_sq = sph_d2_exact(dx, dy, dz);                // (:256)
             if (COUNT && mine) ++visits;
@@ -197,6 +227,259 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int n
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Walk with a pair queue for the sparse part (default; SPH_B200_WALK_DFS=1 selects walk_kernel above).
+//
+// In the shared walk a cell that only a few lanes still have to open costs a full warp iteration per child:
+// at N = 1e6 cells with <= 12 interested lanes are half of all warp iterations but carry a seventh of the
+// particle-cell visits.  Here such a cell is not opened by the warp; instead every (child, target) PAIR goes
+// to a per-warp LIFO queue in shared memory, and whenever 32 pairs are queued one round evaluates them with
+// one pair per lane: the lane fetches its target {x, y, z, h} from the owning lane by shuffle, loads the
+// pair's node, decides the reference's rule for that target exactly as the shared walk does
+// (cell_accepted / leaf_pair are the same code), and either produces the interaction or queues the children
+// of the cell for the same target.  Interactions of a round are added to per-target accumulators in shared
+// memory; pairs of one round that belong to the same target are serialised by their lane rank, so the sums
+// are deterministic.  The set of (particle, node) visits - hence every decision - is the one of the
+// reference; only the summation order differs.
+// The queue can never overflow: a round pops B <= (SOFT - qn) / 7 pairs (each pushes at most 8 children);
+// B = 1 is a depth-first descent whose excursion is bounded by 7 * 21 + 8 entries (the slack above SOFT),
+// and cells are only expanded into the queue while it holds < 32 pairs.
+// ---------------------------------------------------------------------------------------------------
+constexpr int GP_TMAX = 16;              // cells with <= sparse_t <= GP_TMAX interested lanes go to the pair queue
+constexpr int GP_STACK = 160;            // shared stack of dense cells: 7 per level + 8
+constexpr int GP_SOFT = 352;
+constexpr int GP_CAP = GP_SOFT + 160;
+
+struct GpWarp {
+    int2 stack[GP_STACK];                // {first child | nch << 27, lane mask}
+    double4 acc[32];                     // sparse-path sums {gx, gy, gz, phi} of the warp's 32 targets
+    int q[GP_CAP];                       // pairs: node | target lane << 27
+};
+
+// the reference's acceptance rule (:265) for one particle and one internal cell: same arithmetic as walk_kernel
+__device__ __forceinline__ bool cell_accepted(const SphTree &t, int n, double s_sq, double radius, double d_sq,
+                                              double px, double py, double pz, double hi2, double h2x,
+                                              double theta_sq, double th_lo, double th_hi) {
+    // clause 1: s*s/d_sq < theta_sq
+    bool accept;
+    if (s_sq < d_sq * th_lo) accept = true;
+    else if (s_sq > d_sq * th_hi) accept = false;
+    else {
+        asm volatile("");   // see quotient_less
+        accept = s_sq / d_sq < theta_sq;
+    }
+    // clause 2: h_i*h_i / mind2 < 0.25, proven from d > radius + 2 h_i, else the reference's expression
+    if (accept) {
+        const double w = radius + h2x;
+        if (!(d_sq > w * w)) {
+            const double4 B = t.nodeW[GW_REC * (int64_t)n + 2];
+            const double4 C = t.nodeW[GW_REC * (int64_t)n + 3];
+            const double ex = axis_dist_bits(B.x, B.w, px), ey = axis_dist_bits(B.y, C.x, py), ez = axis_dist_bits(B.z, C.y, pz);
+            accept = quotient_less(hi2, sph_d2_exact(ex, ey, ez), 0.25);
+        }
+    }
+    return accept;
+}
+
+// leaf = one particle j with smoothing length hj (:259-264): grad(PHI)/r and PHI per unit mass
+__device__ __forceinline__ void leaf_pair(double d_sq, double hi, double hj, double &gP, double &pot) {
+    const double h_ij = (hi + hj) / 2;                   // (:259)
+    if (d_sq > 4.0 * (h_ij * h_ij)) {                    // q > 2: Newtonian (:19-20)
+        const double rinv = fast_rsqrt(d_sq);
+        gP = rinv * rinv * rinv;
+        pot = -rinv;
+    } else {
+        grav_pair(d_sq, h_ij, gP, pot);
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N, int nranks, int rank, int64_t chunk,
+                                                                       const double4 *__restrict__ pos4, SphTree t,
+                                                                       double theta_sq, double m, int sparse_t,
+                                                                       unsigned long long *__restrict__ scal,
+                                                                       double *__restrict__ part /* [8][4][chunk] */) {
+    __shared__ GpWarp s_w[GW_WARPS];
+    if (scal[SC_ERR] != 0ull) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    GpWarp &sm = s_w[warp];
+    const double4 *__restrict__ W = t.nodeW;
+    const int64_t local = (int64_t)blockIdx.x * (GW_WARPS * 32) + threadIdx.x;
+    const int64_t gtile = ((int64_t)(blockIdx.x / SPH_WALK_DEAL) * nranks + rank) * SPH_WALK_DEAL + blockIdx.x % SPH_WALK_DEAL;
+    const int64_t s = gtile * (GW_WARPS * 32) + threadIdx.x;
+    const bool active = s < N;
+    double px = 0, py = 0, pz = 0, hi = 1.0;
+    if (active) {
+        const double4 p = pos4[s];  // .w = h_i
+        px = p.x; py = p.y; pz = p.z; hi = p.w;
+    }
+    const int sbase = (int)(s - lane);               // sorted slot of lane 0's target
+    const double hi2 = hi * hi;
+    const double h2x = 2.0 * hi * (1.0 + 1e-9);      // clause 2 is certainly true when mindist > h2x
+    const double th_lo = theta_sq * (1.0 - 1e-15), th_hi = theta_sq * (1.0 + 1e-15);
+    double gx = 0.0, gy = 0.0, gz = 0.0, ph = 0.0;
+    unsigned long long visits = 0;
+    const unsigned amask = __ballot_sync(0xffffffffu, active);
+    // the root is opened unconditionally (:246-249); its children are dealt to blockIdx.y (see walk_kernel)
+    const int2 R = unpack_i2(W[1].z);
+    const int rc = walk_root_child(W, R, gtile * (GW_WARPS * 32), blockIdx.y);
+    if (rc < 0) return;
+    sm.acc[lane] = make_double4(0.0, 0.0, 0.0, 0.0);
+    int sp = 0, qn = 0;
+    if (amask) {
+        if (lane == 0) sm.stack[0] = make_int2((R.x + rc) | (1 << 27), (int)amask);
+        sp = 1;
+    }
+    __syncwarp();
+    for (;;) {
+        if (qn >= 32 || (sp == 0 && qn > 0)) {
+            // ---- one round of the pair queue: lane k evaluates pair k of the top B
+            int B = (GP_SOFT - qn) / 7;
+            B = B < 1 ? 1 : (B > 32 ? 32 : B);
+            B = B < qn ? B : qn;
+            qn -= B;
+            const bool v = lane < B;
+            unsigned pr = 0;
+            if (v) pr = (unsigned)sm.q[qn + lane];
+            __syncwarp();
+            const int n = (int)(pr & 0x7ffffffu);
+            const int tl = v ? (int)(pr >> 27) : lane;
+            const double tx = __shfl_sync(0xffffffffu, px, tl), ty = __shfl_sync(0xffffffffu, py, tl),
+                         tz = __shfl_sync(0xffffffffu, pz, tl), th = __shfl_sync(0xffffffffu, hi, tl);
+            double fx = 0.0, fy = 0.0, fz = 0.0, fp = 0.0;
+            bool open = false, has = false;
+            int cfirst = 0, cn = 0;
+            if (v) {
+                const double4 A = W[GW_REC * (int64_t)n], V = W[GW_REC * (int64_t)n + 1];
+                const double dx = tx - A.x, dy = ty - A.y, dz = tz - A.z;   // p_i - rCOM (:255)
+                const double d_sq = sph_d2_exact(dx, dy, dz);                // (:256)
+                if (COUNT) ++visits;
+                const int2 ci = unpack_i2(V.z);
+                if ((ci.y & 0xff) == 0) {
+                    // leaf = particle in sorted slot ci.x; the target's own leaf is skipped (:293-294)
+                    if (ci.x != sbase + tl) {
+                        double gP, pot;
+                        leaf_pair(d_sq, th, A.w, gP, pot);
+                        const double mg = m * gP;
+                        fx = mg * dx; fy = mg * dy; fz = mg * dz;            // (:263)
+                        fp = m * pot;                                        // (:264)
+                        has = true;
+                    }
+                } else if (cell_accepted(t, n, V.x, V.y, d_sq, tx, ty, tz, th * th, 2.0 * th * (1.0 + 1e-9), theta_sq, th_lo, th_hi)) {
+                    const double rinv = fast_rsqrt(d_sq);
+                    const double f = A.w * (rinv * rinv * rinv);             // Mass / d^3  (:266-268)
+                    fx = f * dx; fy = f * dy; fz = f * dz;
+                    fp = -(A.w * rinv);                                      // -Mass / d   (:269)
+                    has = true;
+                } else {
+                    open = true;
+                    cfirst = ci.x; cn = ci.y & 0xff;
+                }
+            }
+            // children of the opened cells: lane k's cell takes cn slots after those of the lanes below it
+            if (__any_sync(0xffffffffu, open)) {
+                int off = cn;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int a = __shfl_up_sync(0xffffffffu, off, o);
+                    if (lane >= o) off += a;
+                }
+                const int total = __shfl_sync(0xffffffffu, off, 31);
+                int *dst = sm.q + (qn + off - cn);
+                const unsigned tag = (unsigned)tl << 27;
+#pragma unroll 1
+                for (int c = 0; c < cn; ++c) dst[c] = (int)((unsigned)(cfirst + c) | tag);
+                qn += total;
+            }
+            // interactions -> per-target sums; pairs of the same target take turns in lane order
+            const unsigned peers = __match_any_sync(0xffffffffu, has ? tl : 32 + lane);
+            const int prank = __popc(peers & lt);
+            const int mult = __reduce_max_sync(0xffffffffu, has ? __popc(peers) : 0);
+            for (int r = 0; r < mult; ++r) {
+                if (has && prank == r) {
+                    double4 a = sm.acc[tl];
+                    a.x += fx; a.y += fy; a.z += fz; a.w += fp;
+                    sm.acc[tl] = a;
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+            continue;
+        }
+        if (sp == 0) break;
+        const int2 top = sm.stack[--sp];
+        __syncwarp();
+        const unsigned mask = (unsigned)top.y;
+        const bool mine = (mask >> lane) & 1u;
+        const int first = top.x & 0x7ffffff, nch = top.x >> 27;
+        const int pc = __popc(mask);
+        if (pc <= sparse_t) {
+            // few lanes are interested: their (child, target) pairs go to the queue, child-major (qn < 32 here)
+            if (mine) {
+                const int r = __popc(mask & lt);
+                for (int c = 0; c < nch; ++c) sm.q[qn + c * pc + r] = (int)((unsigned)(first + c) | ((unsigned)lane << 27));
+            }
+            qn += pc * nch;
+            __syncwarp();
+            continue;
+        }
+        if (sp + nch > GP_STACK) {  // cannot happen for depth <= 21; never write out of bounds
+            if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)ERRF_STACK);
+            break;
+        }
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+            const int n = first + c;
+            const double4 A = W[GW_REC * (int64_t)n], V = W[GW_REC * (int64_t)n + 1];   // A = {rCOM, Mass | h_j}, V = {(2L)^2, radius, child info, range}
+            const double dx = px - A.x, dy = py - A.y, dz = pz - A.z;   // p_i - rCOM (:255)
+            const double d_sq = sph_d2_exact(dx, dy, dz);                // (:256)
+            if (COUNT && mine) ++visits;
+            const int2 ci = unpack_i2(V.z);
+            if ((ci.y & 0xff) == 0) {
+                // leaf = one particle j; A.w carries h_j, its mass is m; the target's own leaf is skipped (:293-294)
+                if (mine && ci.x != sbase + lane) {
+                    double gP, pot;
+                    leaf_pair(d_sq, hi, A.w, gP, pot);
+                    const double mg = m * gP;
+                    gx += mg * dx; gy += mg * dy; gz += mg * dz;         // (:263)
+                    ph += m * pot;                                       // (:264)
+                }
+            } else {
+                bool open = false;
+                if (mine) {
+                    if (cell_accepted(t, n, V.x, V.y, d_sq, px, py, pz, hi2, h2x, theta_sq, th_lo, th_hi)) {
+                        const double rinv = fast_rsqrt(d_sq);
+                        const double f = A.w * (rinv * rinv * rinv);         // Mass / d^3  (:266-268)
+                        gx += f * dx; gy += f * dy; gz += f * dz;
+                        ph -= A.w * rinv;                                    // -Mass / d   (:269)
+                    } else {
+                        open = true;
+                    }
+                }
+                const unsigned om = __ballot_sync(0xffffffffu, open);
+                if (om) {
+                    if (lane == 0) sm.stack[sp] = make_int2(ci.x | ((ci.y & 0xff) << 27), (int)om);
+                    ++sp;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (active) {
+        const double4 a = sm.acc[lane];
+        gx += a.x; gy += a.y; gz += a.z; ph += a.w;
+        double *out = part + (size_t)rc * 4 * chunk;
+        out[local] = gx; out[local + chunk] = gy; out[local + 2 * chunk] = gz;
+        out[local + 3 * chunk] = rc == 0 ? ph - (m * (7.0 / 5) / hi) : ph;        // (:303), once
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
+        if (lane == 0) atomicAdd(scal + SC_VISITS, visits);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Batched walk (opt-in: SPH_B200_WALK_BATCH=1).  Same decisions and the same per-lane arithmetic as walk_kernel above, but the
 // warp pops up to 32 cells per round: lane k fetches the 64-byte record of cell k (coalesced-ish: siblings
 // are contiguous) and parks it in shared memory; then every lane - one target each - runs over the parked
@@ -243,9 +526,9 @@ __global__ void __launch_bounds__(GB_WARPS * 32, 4) walk_batch_kernel(int64_t N,
     unsigned long long visits = 0;
     const unsigned amask = __ballot_sync(0xffffffffu, active);
     // the root is opened unconditionally (:246-249); its children are dealt to blockIdx.y (see walk_kernel)
-    const int rc = blockIdx.y;
     const int2 R = unpack_i2(W[1].z);
-    if (rc >= (R.y & 0xff)) return;
+    const int rc = walk_root_child(W, R, gtile * (GB_WARPS * 32), blockIdx.y);
+    if (rc < 0) return;
     int sp = 0;
     if (amask) {
         if (lane == 0) sm.stack[0] = make_int2((R.x + rc) | (int)((((unsigned)(R.y >> 8) >> rc) & 1u) << 31), (int)amask);
@@ -263,8 +546,8 @@ __global__ void __launch_bounds__(GB_WARPS * 32, 4) walk_batch_kernel(int64_t N,
         if (lane < B) {
             e = sm.stack[sp + lane];
             const int64_t n = e.x & 0x7fffffff;
-            A = W[2 * n];
-            V = W[2 * n + 1];
+            A = W[GW_REC * n];
+            V = W[GW_REC * n + 1];
             sm.recA[lane] = A; sm.recV[lane] = V; sm.ent[lane] = e;
         }
         __syncwarp();
@@ -381,8 +664,13 @@ __global__ void pack_nodes_kernel(SphTree t, const double4 *__restrict__ pos4, c
         double2 D = make_double2(0.0, 0.0);
         if (I.y == 0) A.w = pos4[I.x].w;
         else D = t.nodeD[k];
-        t.nodeW[2 * k] = A;
-        t.nodeW[2 * k + 1] = make_double4(D.x, D.y, pack_i2(I.x, I.y), pack_i2(t.nstart[k], t.ncount[k]));
+        double4 *rec = t.nodeW + GW_REC * k;
+        rec[0] = A;
+        rec[1] = make_double4(D.x, D.y, pack_i2(I.x, I.y), pack_i2(t.nstart[k], t.ncount[k]));
+        if (I.y != 0) {           // cell bounds for the exact evaluation of clause 2, in the same 128-byte line
+            rec[2] = t.nodeB[k];
+            rec[3] = t.nodeC[k];
+        }
     }
 }
 
@@ -403,6 +691,13 @@ cudaError_t sph_launch_walk(sph_handle *h) {
     static const bool count = getenv("SPH_B200_COUNT_VISITS") != nullptr;
     // the batched walk (walk_batch_kernel) measures the same as the depth-first walk; it stays opt-in
     static const bool dfs = getenv("SPH_B200_WALK_BATCH") == nullptr;
+    static const bool shared_only = getenv("SPH_B200_WALK_DFS") != nullptr;
+    // cells with <= sparse_t interested lanes are evaluated pair-wise (walk_pairs_kernel); 0 = never
+    static const int sparse_t = [] {
+        const char *e = getenv("SPH_B200_WALK_T");
+        const int v = e ? atoi(e) : 12;
+        return v < 0 ? 0 : (v > GP_TMAX ? GP_TMAX : v);
+    }();
     if (!dfs) {
         static bool attr_set = false;
         const size_t smem = sizeof(GbWarp) * GB_WARPS;
@@ -419,12 +714,31 @@ cudaError_t sph_launch_walk(sph_handle *h) {
         else
             walk_batch_kernel<false><<<grid, GB_WARPS * 32, smem, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4,
                                                                                h->tree, th2, lo, hi, h->p.m, h->scal, h->walk_part);
-    } else if (count)
-        walk_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
-                                                                 th2, h->p.m, h->scal, h->walk_part);
+    } else if (shared_only || h->tree.cap >= (1ll << 27) || h->N >= (1ll << 31)) {
+        // the shared depth-first walk alone (SPH_B200_WALK_DFS=1, or node ids that do not fit the pair encoding)
+        if (count)
+            walk_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+                                                                     th2, h->p.m, h->scal, h->walk_part);
+        else
+            walk_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+                                                                      th2, h->p.m, h->scal, h->walk_part);
+    } else {
+        static const bool carve_set = [] {   // experiment: shared-memory carve-out (percent of the maximum) of the pair walk
+            const char *e = getenv("SPH_B200_WALK_CARVE");
+            if (e) {
+                cudaFuncSetAttribute(walk_pairs_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+                cudaFuncSetAttribute(walk_pairs_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+            }
+            return true;
+        }();
+        (void)carve_set;
+        if (count)
+        walk_pairs_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+                                                                       th2, h->p.m, sparse_t, h->scal, h->walk_part);
     else
-        walk_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
-                                                                  th2, h->p.m, h->scal, h->walk_part);
+        walk_pairs_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+                                                                        th2, h->p.m, sparse_t, h->scal, h->walk_part);
+    }
     walk_reduce_kernel<<<148 * 8, 256, 0, h->stream>>>(4 * h->walk_chunk, h->walk_part, h->tree.nodeW, h->scal, out);
     return cudaGetLastError();
 }

@@ -291,7 +291,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
         if (const char *e = getenv("SPH_B200_NODE_FACTOR")) factor = atof(e) > 1.5 ? atof(e) : 3.0;
         t.cap = (int64_t)(factor * (double)N) + 1024;
         const size_t C = (size_t)t.cap;
-        CK(dalloc(&t.nodeI, C)); CK(dalloc(&t.nodeA, C)); CK(dalloc(&t.nodeB, C)); CK(dalloc(&t.nodeC, C)); CK(dalloc(&t.nodeD, C)); CK(dalloc(&t.nodeW, 2 * C));
+        CK(dalloc(&t.nodeI, C)); CK(dalloc(&t.nodeA, C)); CK(dalloc(&t.nodeB, C)); CK(dalloc(&t.nodeC, C)); CK(dalloc(&t.nodeD, C)); CK(dalloc(&t.nodeW, SPH_WALK_REC * C));
         CK(dalloc(&t.nstart, C)); CK(dalloc(&t.ncount, C)); CK(dalloc(&t.ndepth, C));
         CK(dalloc(&t.parent, C)); CK(dalloc(&t.arrive, C));
         CK(dalloc(&t.old_start, C)); CK(dalloc(&t.old_depth, C));

@@ -18,6 +18,7 @@
 
 #define SPH_LEVELS 21           // octant levels held by one 63-bit key
 #define SPH_MAX_RANKS 16
+#define SPH_WALK_REC 4           // double4 per walk record of the octree (one 128-byte line per node)
 #define SPH_WALK_DEAL 16         // walk tiles (128 targets) are dealt to the ranks in groups of 16 consecutive tiles:
                                  // round-robin balances the load, consecutive tiles keep the tree nodes hot in L2
 
@@ -119,7 +120,7 @@ struct SphTree {
     int64_t cap = 0;  // node capacity
     int2 *nodeI = nullptr;
     double4 *nodeA = nullptr, *nodeB = nullptr, *nodeC = nullptr;
-    double4 *nodeW = nullptr;  // walk records, 2 x double4 per node: {com.xyz, mass | h_j}, {(2L)^2, radius, bits{first|slot, nch|leafmask<<8}, bits{nstart, ncount}}
+    double4 *nodeW = nullptr;  // walk records, SPH_WALK_REC x double4 per node: {com.xyz, mass | h_j}, {(2L)^2, radius, bits{first|slot, nch|leafmask<<8}, bits{nstart, ncount}}, nodeB, nodeC
     double2 *nodeD = nullptr;  // internal nodes: {(2 Length)^2, upper bound of the distance from rCOM to any point of the cell}
     int *nstart = nullptr, *ncount = nullptr, *ndepth = nullptr;
     int *parent = nullptr, *arrive = nullptr;   // bottom-up COM sweep: parent id, number of finished children
