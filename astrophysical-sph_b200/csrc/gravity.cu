@@ -682,7 +682,12 @@ cudaError_t sph_launch_walk(sph_handle *h) {
     pack_nodes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->tree, h->pos4, h->scal);
     const int64_t tiles = (h->N + 127) / 128;
     const int64_t groups = (tiles + SPH_WALK_DEAL - 1) / SPH_WALK_DEAL;
-    const int64_t blocks = (groups - h->rank + h->nranks - 1) / h->nranks * SPH_WALK_DEAL;   // groups rank, rank + P, ...
+    // SPH_B200_WALK_FAKE_RANKS=P (timing experiments on one GPU only): walk the share rank 0 would own among P ranks;
+    // the other targets keep stale results
+    static const int fake_ranks = getenv("SPH_B200_WALK_FAKE_RANKS") ? atoi(getenv("SPH_B200_WALK_FAKE_RANKS")) : 0;
+    const int w_nranks = fake_ranks > 0 && h->nranks == 1 ? fake_ranks : h->nranks;
+    const int w_rank = h->rank;
+    const int64_t blocks = (groups - w_rank + w_nranks - 1) / w_nranks * SPH_WALK_DEAL;   // groups rank, rank + P, ...
     if (blocks <= 0) return cudaGetLastError();
     const double th2 = h->p.theta * h->p.theta;
     double *out = h->walk_buf + (size_t)h->rank * 4 * h->walk_chunk;
@@ -709,18 +714,18 @@ cudaError_t sph_launch_walk(sph_handle *h) {
         }
         const double lo = th2 * (1.0 - 1e-15), hi = th2 * (1.0 + 1e-15);
         if (count)
-            walk_batch_kernel<true><<<grid, GB_WARPS * 32, smem, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4,
+            walk_batch_kernel<true><<<grid, GB_WARPS * 32, smem, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4,
                                                                               h->tree, th2, lo, hi, h->p.m, h->scal, h->walk_part);
         else
-            walk_batch_kernel<false><<<grid, GB_WARPS * 32, smem, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4,
+            walk_batch_kernel<false><<<grid, GB_WARPS * 32, smem, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4,
                                                                                h->tree, th2, lo, hi, h->p.m, h->scal, h->walk_part);
     } else if (shared_only || h->tree.cap >= (1ll << 27) || h->N >= (1ll << 31)) {
         // the shared depth-first walk alone (SPH_B200_WALK_DFS=1, or node ids that do not fit the pair encoding)
         if (count)
-            walk_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+            walk_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4, h->tree,
                                                                      th2, h->p.m, h->scal, h->walk_part);
         else
-            walk_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+            walk_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4, h->tree,
                                                                       th2, h->p.m, h->scal, h->walk_part);
     } else {
         static const bool carve_set = [] {   // experiment: shared-memory carve-out (percent of the maximum) of the pair walk
@@ -733,10 +738,10 @@ cudaError_t sph_launch_walk(sph_handle *h) {
         }();
         (void)carve_set;
         if (count)
-        walk_pairs_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+        walk_pairs_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4, h->tree,
                                                                        th2, h->p.m, sparse_t, h->scal, h->walk_part);
     else
-        walk_pairs_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+        walk_pairs_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4, h->tree,
                                                                         th2, h->p.m, sparse_t, h->scal, h->walk_part);
     }
     walk_reduce_kernel<<<148 * 8, 256, 0, h->stream>>>(4 * h->walk_chunk, h->walk_part, h->tree.nodeW, h->scal, out);

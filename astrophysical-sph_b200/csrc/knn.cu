@@ -290,6 +290,7 @@ constexpr int KQ_WARPS = 5;
 constexpr int KQ_BUCKET = 64;   // cells up to this size are scanned as ranges (fewer dependent node loads than 32)
 constexpr int KQ_BKS = 64;      // buckets gathered before a flush
 constexpr int KQ_CAND = 768;    // candidates gathered before a flush
+constexpr int KQ_SEL_STEPS = 8;  // selection steps around the previous K-th distance before the sort takes over
 constexpr int KQ_MAXCAND = 3072; // quads whose box spans more candidates (key-order jumps) go to the per-target search
 
 struct KqWarp {
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
                                                                     const double4 *__restrict__ pos4,
                                                                     const int *__restrict__ perm, SphTree t,
                                                                     const double *__restrict__ hint_h, double hint_fac2,
-                                                                    unsigned long long *__restrict__ scal,
+                                                                    int sel_steps, unsigned long long *__restrict__ scal,
                                                                     int *__restrict__ retry_list,
                                                                     int *__restrict__ nbr, double *__restrict__ d2k) {
     __shared__ KqWarp s_w[KQ_WARPS];
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
     const double ldom = __longlong_as_double((long long)scal[SC_LDOM]);
     const double eps = ldom * 1e-14;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const double inv_fac2 = 1.0 / hint_fac2;
 
     const int64_t nquads = (t1 - t0 + KQ_T - 1) / KQ_T;
     for (int64_t quad = (int64_t)blockIdx.x * KQ_WARPS + warp; quad < nquads; quad += (int64_t)gridDim.x * KQ_WARPS) {
@@ -349,13 +351,15 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
         }
         // ---- one walk for the 4 balls (all values above are warp-uniform)
         if (any) {
-            int sp = 1, nb = 0, ncand = 0, tested = 0;
+            int sp = 1, nb = 0, ncand = 0, tested = 0, width = 4;
+            bool flush_now = false;
             if (lane == 0) sm.stack[0] = 0;
             __syncwarp();
             for (;;) {
                 const bool last = sp == 0;
                 // ---- flush: expand the gathered buckets into a dense candidate list and test it in rounds of 32
-                if (nb > 0 && (last || nb + 8 > KQ_BKS || ncand + 8 * KQ_BUCKET > KQ_CAND)) {
+                if (nb > 0 && (last || flush_now)) {
+                    flush_now = false;
                     tested += ncand;
                     if (tested > KQ_MAXCAND) {
                         // the box of these 4 targets straddles a jump of the key order: four small balls are cheaper
@@ -404,14 +408,23 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
                     nb = 0; ncand = 0;
                 }
                 if (last) break;
-                const int n = sm.stack[--sp];
-                __syncwarp();
-                const int2 I = t.nodeI[n];
+                // ---- pop up to 4 cells: lane group g = lane / 8 tests the (up to 8) children of cell g
+                int m = width < sp ? width : sp;
+                if (sp - m + 8 * m > KNN_STACK) m = 1;
+                if (sp + 7 > KNN_STACK) {   // cannot happen for these pruned walks; never write out of bounds
+                    if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)ERRF_STACK);
+#pragma unroll
+                    for (int k = 0; k < KQ_T; ++k) ok[k] = false;
+                    break;
+                }
+                const int g = lane >> 3, c8 = lane & 7;
+                int2 I = make_int2(0, 0);
+                if (g < m) I = t.nodeI[sm.stack[sp - 1 - g]];
                 const int nch = I.y & 0xff, first = I.x;
                 bool pass = false;
                 int cstart = 0, ccount = 0;
-                if (lane < nch) {
-                    const int c = first + lane;
+                if (c8 < nch) {
+                    const int c = first + c8;
                     const double4 B = t.nodeB[c];
                     const double4 C = t.nodeC[c];
                     pass = B.x <= bhi[0] && B.w >= blo[0] && B.y <= bhi[1] && C.x >= blo[1] && B.z <= bhi[2] && C.y >= blo[2];
@@ -421,14 +434,22 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
                 const bool is_bucket = ccount <= KQ_BUCKET;
                 const unsigned bm = __ballot_sync(0xffffffffu, pass && is_bucket);
                 const unsigned im = __ballot_sync(0xffffffffu, pass && !is_bucket);
-                if (pass && !is_bucket) sm.stack[sp + __popc(im & lt)] = first + lane;
+                const int add = __reduce_add_sync(0xffffffffu, (pass && is_bucket) ? ccount : 0);
+                if (nb + __popc(bm) > KQ_BKS || ncand + add > KQ_CAND) {
+                    // does not fit: test what is gathered and come back (nothing was consumed); the children of a
+                    // single cell always fit the empty lists (8 buckets, 8 * KQ_BUCKET candidates)
+                    if (nb > 0) flush_now = true;
+                    else width = 1;
+                    continue;
+                }
+                __syncwarp();   // every group has read its stack entry before the pushes reuse the slots
+                sp -= m;
+                if (pass && !is_bucket) sm.stack[sp + __popc(im & lt)] = first + c8;
                 sp += __popc(im);
                 if (pass && is_bucket) sm.bks[nb + __popc(bm & lt)] = make_int2(cstart, ccount);
                 nb += __popc(bm);
-                int add = (pass && is_bucket) ? ccount : 0;
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);   // children sit in lanes 0..7
-                ncand += __shfl_sync(0xffffffffu, add, 0);
+                ncand += add;
+                width = 4;
                 __syncwarp();
             }
         }
@@ -444,7 +465,75 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
             const double *bd2 = sm.d2[k];
             const int *bid = sm.id[k];
             bool tie = false;
-            if (n <= 64) {
+            // ---- selection instead of a sort: the lists need no order (density / force skip the self entry by index,
+            // the export sorts on demand).  Keys are the bit patterns of the squared distances (order-preserving).
+            // The K-th smallest is reached from the previous evaluation's K-th distance (2 h_prev)^2 by stepping over
+            // distinct key values and recounting; between two evaluations the count inside that radius moves by a few.
+            bool found = false;
+            {
+                unsigned long long key[KQ_CAP / 32];
+                int vid[KQ_CAP / 32];
+#pragma unroll
+                for (int r = 0; r < KQ_CAP / 32; ++r) {
+                    const int e = lane + 32 * r;
+                    key[r] = e < n ? (unsigned long long)__double_as_longlong(bd2[e]) : ~0ull;
+                    vid[r] = e < n ? bid[e] : -1;
+                }
+                unsigned long long cur = (unsigned long long)__double_as_longlong(R2[k] * inv_fac2), kth = 0;
+                int cl = 0;
+#pragma unroll
+                for (int r = 0; r < KQ_CAP / 32; ++r) cl += key[r] <= cur;
+                int c = __reduce_add_sync(0xffffffffu, cl);
+                if (c < K) {
+                    // the (K - c)-th distinct value above cur, at most KQ_SEL_STEPS steps
+                    for (int it = 0; it < sel_steps && !found; ++it) {
+                        unsigned long long mn = ~0ull;
+#pragma unroll
+                        for (int r = 0; r < KQ_CAP / 32; ++r)
+                            if (key[r] > cur && key[r] < mn) mn = key[r];
+                        const unsigned mh = __reduce_min_sync(0xffffffffu, (unsigned)(mn >> 32));
+                        const unsigned ml = __reduce_min_sync(0xffffffffu, (unsigned)(mn >> 32) == mh ? (unsigned)mn : 0xffffffffu);
+                        cur = ((unsigned long long)mh << 32) | ml;
+                        cl = 0;
+#pragma unroll
+                        for (int r = 0; r < KQ_CAP / 32; ++r) cl += key[r] <= cur;
+                        c = __reduce_add_sync(0xffffffffu, cl);
+                        if (c >= K) { found = true; kth = cur; tie = c > K; }
+                    }
+                } else {
+                    // walk down over the distinct values <= cur until fewer than K keys lie below
+                    for (int it = 0; it < sel_steps && !found; ++it) {
+                        unsigned long long mx = 0ull;
+#pragma unroll
+                        for (int r = 0; r < KQ_CAP / 32; ++r)
+                            if (key[r] <= cur && key[r] > mx) mx = key[r];
+                        const unsigned mh = __reduce_max_sync(0xffffffffu, (unsigned)(mx >> 32));
+                        const unsigned ml = __reduce_max_sync(0xffffffffu, (unsigned)(mx >> 32) == mh ? (unsigned)mx : 0u);
+                        mx = ((unsigned long long)mh << 32) | ml;
+                        cl = 0;
+#pragma unroll
+                        for (int r = 0; r < KQ_CAP / 32; ++r) cl += key[r] == mx;
+                        const int ceq = __reduce_add_sync(0xffffffffu, cl);
+                        if (c - ceq < K) { found = true; kth = mx; tie = c > K; }
+                        else { c -= ceq; cur = mx - 1ull; }   // mx > 0 here: the keys equal to 0 alone never reach K
+                    }
+                }
+                if (found && !tie) {
+                    // emit the keys <= kth in buffer order (exactly K of them)
+                    int base = 0;
+#pragma unroll
+                    for (int r = 0; r < KQ_CAP / 32; ++r) {
+                        const bool sel = key[r] <= kth;
+                        const unsigned sb = __ballot_sync(0xffffffffu, sel);
+                        if (sel) nbr[s + (int64_t)(base + __popc(sb & lt)) * N] = vid[r];
+                        base += __popc(sb);
+                    }
+                    if (lane == 0) d2k[s] = __longlong_as_double((long long)kth);
+                }
+            }
+            if (found) {
+                // tie at the K-th distance: the exact tie-breaking path decides (below)
+            } else if (n <= 64) {
                 // register bitonic sort of 64 keys (element e = lane + 32 r), shuffles for the 5 low strides
                 unsigned long long k0 = lane < n ? (unsigned long long)__double_as_longlong(bd2[lane]) : ~0ull;
                 unsigned long long k1 = lane + 32 < n ? (unsigned long long)__double_as_longlong(bd2[lane + 32]) : ~0ull;
@@ -547,8 +636,10 @@ cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1) {
         const int64_t quads = (t1 - t0 + KQ_T - 1) / KQ_T;
         int64_t blocks = (quads + KQ_WARPS - 1) / KQ_WARPS;
         if (blocks > 148 * 5 * 8) blocks = 148 * 5 * 8;
+        // SPH_B200_KNN_SORT=1: always order the hits with the sort network instead of selecting the K-th distance
+        static const int sel_steps = getenv("SPH_B200_KNN_SORT") ? 0 : KQ_SEL_STEPS;
         knn_quad_kernel<<<(int)blocks, KQ_WARPS * 32, 0, h->stream>>>(h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2,
-                                                                     h->scal, h->cnt, h->nbr, h->d2k);
+                                                                     sel_steps, h->scal, h->cnt, h->nbr, h->d2k);
         // queued targets keep their own hinted ball (only the shared box was too wide); a failing hint falls back to
         // the guaranteed radius inside the kernel
         knn_kernel<128, true><<<148 * 5, KNN_WARPS * 32, 0, h->stream>>>(
