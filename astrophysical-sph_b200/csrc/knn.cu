@@ -287,9 +287,11 @@ __global__ void point_density_kernel(int64_t M, int K, const double *__restrict_
 constexpr int KQ_T = 4;
 constexpr int KQ_CAP = 96;
 constexpr int KQ_WARPS = 5;
-constexpr int KQ_BUCKET = 64;   // cells up to this size are scanned as ranges (fewer dependent node loads than 32)
+constexpr int KQ_BLOCKS = 4;     // resident blocks per SM (5 fit, but leave no L1 next to their shared memory: 3.0 vs 2.5 ms)
+constexpr int KQ_BUCKET = 64;   // largest cell scanned as a range (list sizing); the default threshold is 32 (SPH_B200_KNN_BUCKET)
 constexpr int KQ_BKS = 64;      // buckets gathered before a flush
-constexpr int KQ_CAND = 768;    // candidates gathered before a flush
+constexpr int KQ_CAND = 512;    // candidates gathered before a flush (>= 8 * KQ_BUCKET)
+constexpr int KQ_STACK = 96;    // cells to visit; a walk that needs more hands its targets to the per-target search
 constexpr int KQ_SEL_STEPS = 8;  // selection steps around the previous K-th distance before the sort takes over
 constexpr int KQ_MAXCAND = 3072; // quads whose box spans more candidates (key-order jumps) go to the per-target search
 
@@ -298,7 +300,7 @@ struct KqWarp {
     int id[KQ_T][KQ_CAP];
     int2 bks[KQ_BKS];
     int cand[KQ_CAND];
-    int stack[KNN_STACK];
+    int2 stack[KQ_STACK];   // {first child, number of children} of the cells still to visit
 };
 
 // compare-exchange step of the register bitonic sort: keys are the bit patterns of non-negative doubles
@@ -307,11 +309,12 @@ __device__ __forceinline__ void kq_cex(unsigned long long &k, int &v, unsigned l
     if (other_smaller == keep_small) { k = ok; v = ov; }
 }
 
-__global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, int K, int64_t t0, int64_t t1,
+template <int BLOCKS>
+__global__ void __launch_bounds__(KQ_WARPS * 32, BLOCKS) knn_quad_kernel(int64_t N, int K, int64_t t0, int64_t t1,
                                                                     const double4 *__restrict__ pos4,
                                                                     const int *__restrict__ perm, SphTree t,
                                                                     const double *__restrict__ hint_h, double hint_fac2,
-                                                                    int sel_steps, unsigned long long *__restrict__ scal,
+                                                                    int sel_steps, int bucket, unsigned long long *__restrict__ scal,
                                                                     int *__restrict__ retry_list,
                                                                     int *__restrict__ nbr, double *__restrict__ d2k) {
     __shared__ KqWarp s_w[KQ_WARPS];
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
         if (any) {
             int sp = 1, nb = 0, ncand = 0, tested = 0, width = 4;
             bool flush_now = false;
-            if (lane == 0) sm.stack[0] = 0;
+            if (lane == 0) { const int2 I0 = t.nodeI[0]; sm.stack[0] = make_int2(I0.x, I0.y & 0xff); }
             __syncwarp();
             for (;;) {
                 const bool last = sp == 0;
@@ -383,15 +386,15 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
                         for (int i = 0; i < c1; ++i) o1[i] = st1 + i;
                     }
                     __syncwarp();
+                    // the positions of the next 32 candidates are requested before the current ones are tested
+                    int jn = 0;
+                    double4 pn = make_double4(0.0, 0.0, 0.0, 0.0);
+                    if (lane < ncand) { jn = sm.cand[lane]; pn = pos4[jn]; }
                     for (int base = 0; base < ncand; base += 32) {
                         const bool v = base + lane < ncand;
-                        int j = 0;
-                        double px = 0.0, py = 0.0, pz = 0.0;
-                        if (v) {
-                            j = sm.cand[base + lane];
-                            const double4 p = pos4[j];
-                            px = p.x; py = p.y; pz = p.z;
-                        }
+                        const int j = jn;
+                        const double px = pn.x, py = pn.y, pz = pn.z;
+                        if (base + 32 + lane < ncand) { jn = sm.cand[base + 32 + lane]; pn = pos4[jn]; }
 #pragma unroll
                         for (int k = 0; k < KQ_T; ++k) {
                             const double d2 = sph_d2_exact(qx[k] - px, qy[k] - py, qz[k] - pz);
@@ -410,28 +413,29 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
                 if (last) break;
                 // ---- pop up to 4 cells: lane group g = lane / 8 tests the (up to 8) children of cell g
                 int m = width < sp ? width : sp;
-                if (sp - m + 8 * m > KNN_STACK) m = 1;
-                if (sp + 7 > KNN_STACK) {   // cannot happen for these pruned walks; never write out of bounds
-                    if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)ERRF_STACK);
+                if (sp - m + 8 * m > KQ_STACK) m = 1;
+                if (sp + 7 > KQ_STACK) {   // not seen for these pruned walks: the per-target search takes the four targets
 #pragma unroll
                     for (int k = 0; k < KQ_T; ++k) ok[k] = false;
                     break;
                 }
                 const int g = lane >> 3, c8 = lane & 7;
                 int2 I = make_int2(0, 0);
-                if (g < m) I = t.nodeI[sm.stack[sp - 1 - g]];
-                const int nch = I.y & 0xff, first = I.x;
+                if (g < m) I = sm.stack[sp - 1 - g];
+                const int nch = I.y, first = I.x;
                 bool pass = false;
                 int cstart = 0, ccount = 0;
+                int2 Ic = make_int2(0, 0);     // the child's own children: fetched with its box, so a pop needs no dependent load
                 if (c8 < nch) {
                     const int c = first + c8;
+                    Ic = t.nodeI[c];
                     const double4 B = t.nodeB[c];
                     const double4 C = t.nodeC[c];
                     pass = B.x <= bhi[0] && B.w >= blo[0] && B.y <= bhi[1] && C.x >= blo[1] && B.z <= bhi[2] && C.y >= blo[2];
                     cstart = t.nstart[c];
                     ccount = t.ncount[c];
                 }
-                const bool is_bucket = ccount <= KQ_BUCKET;
+                const bool is_bucket = ccount <= bucket;
                 const unsigned bm = __ballot_sync(0xffffffffu, pass && is_bucket);
                 const unsigned im = __ballot_sync(0xffffffffu, pass && !is_bucket);
                 const int add = __reduce_add_sync(0xffffffffu, (pass && is_bucket) ? ccount : 0);
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, 4) knn_quad_kernel(int64_t N, i
                 }
                 __syncwarp();   // every group has read its stack entry before the pushes reuse the slots
                 sp -= m;
-                if (pass && !is_bucket) sm.stack[sp + __popc(im & lt)] = first + c8;
+                if (pass && !is_bucket) sm.stack[sp + __popc(im & lt)] = make_int2(Ic.x, Ic.y & 0xff);
                 sp += __popc(im);
                 if (pass && is_bucket) sm.bks[nb + __popc(bm & lt)] = make_int2(cstart, ccount);
                 nb += __popc(bm);
@@ -638,8 +642,19 @@ cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1) {
         if (blocks > 148 * 5 * 8) blocks = 148 * 5 * 8;
         // SPH_B200_KNN_SORT=1: always order the hits with the sort network instead of selecting the K-th distance
         static const int sel_steps = getenv("SPH_B200_KNN_SORT") ? 0 : KQ_SEL_STEPS;
-        knn_quad_kernel<<<(int)blocks, KQ_WARPS * 32, 0, h->stream>>>(h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2,
-                                                                     sel_steps, h->scal, h->cnt, h->nbr, h->d2k);
+        // cells up to this many particles are scanned as ranges (<= KQ_BUCKET: the lists are sized for 8 such cells)
+        static const int bucket = [] {
+            const char *e = getenv("SPH_B200_KNN_BUCKET");
+            const int v = e ? atoi(e) : 32;
+            return v < 1 ? 1 : (v > KQ_BUCKET ? KQ_BUCKET : v);
+        }();
+        static const bool five = getenv("SPH_B200_KNN_BLOCKS5") != nullptr;   // experiment: 5 resident blocks, 80 registers
+        if (five)
+            knn_quad_kernel<5><<<(int)blocks, KQ_WARPS * 32, 0, h->stream>>>(h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2,
+                                                                            sel_steps, bucket, h->scal, h->cnt, h->nbr, h->d2k);
+        else
+            knn_quad_kernel<KQ_BLOCKS><<<(int)blocks, KQ_WARPS * 32, 0, h->stream>>>(h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2,
+                                                                                    sel_steps, bucket, h->scal, h->cnt, h->nbr, h->d2k);
         // queued targets keep their own hinted ball (only the shared box was too wide); a failing hint falls back to
         // the guaranteed radius inside the kernel
         knn_kernel<128, true><<<148 * 5, KNN_WARPS * 32, 0, h->stream>>>(
