@@ -295,8 +295,8 @@ __device__ __forceinline__ void leaf_pair(double d_sq, double hi, double hj, dou
 template <bool COUNT>
 __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N, int nranks, int rank, int64_t chunk,
                                                                        const double4 *__restrict__ pos4, SphTree t,
-                                                                       double theta_sq, double m, int sparse_t,
-                                                                       unsigned long long *__restrict__ scal,
+                                                                       double theta_sq, double th_lo, double th_hi, double m,
+                                                                       int sparse_t, unsigned long long *__restrict__ scal,
                                                                        double *__restrict__ part /* [8][4][chunk] */) {
     __shared__ GpWarp s_w[GW_WARPS];
     if (scal[SC_ERR] != 0ull) return;
@@ -316,7 +316,6 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N,
     const int sbase = (int)(s - lane);               // sorted slot of lane 0's target
     const double hi2 = hi * hi;
     const double h2x = 2.0 * hi * (1.0 + 1e-9);      // clause 2 is certainly true when mindist > h2x
-    const double th_lo = theta_sq * (1.0 - 1e-15), th_hi = theta_sq * (1.0 + 1e-15);
     double gx = 0.0, gy = 0.0, gz = 0.0, ph = 0.0;
     unsigned long long visits = 0;
     const unsigned amask = __ballot_sync(0xffffffffu, active);
@@ -739,10 +738,10 @@ cudaError_t sph_launch_walk(sph_handle *h) {
         (void)carve_set;
         if (count)
         walk_pairs_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4, h->tree,
-                                                                       th2, h->p.m, sparse_t, h->scal, h->walk_part);
+                                                                       th2, th2 * (1.0 - 1e-15), th2 * (1.0 + 1e-15), h->p.m, sparse_t, h->scal, h->walk_part);
     else
         walk_pairs_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4, h->tree,
-                                                                        th2, h->p.m, sparse_t, h->scal, h->walk_part);
+                                                                        th2, th2 * (1.0 - 1e-15), th2 * (1.0 + 1e-15), h->p.m, sparse_t, h->scal, h->walk_part);
     }
     walk_reduce_kernel<<<148 * 8, 256, 0, h->stream>>>(4 * h->walk_chunk, h->walk_part, h->tree.nodeW, h->scal, out);
     return cudaGetLastError();

@@ -257,12 +257,16 @@ def run_b200(args, rank, world, local_rank):
                 "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "sph_upload + sph_step(1) + sph_download on pinned host buffers, every step"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": {"knn": "knn_kernel", "gravity": "walk_kernel", "force": "force_kernel",
+        "roofline": {"bound": "hbm", "kernel": {"knn": "knn_quad_kernel", "gravity": "walk_pairs_kernel", "force": "force_kernel",
                                                 "density": "density_kernel"}[dom],
                      "achieved": phases[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": phases[dom]["frac"],
                      "traffic": traffic, "peak_source": peak_src,
                      "note": "algorithmic bytes per SURVEY.md 8(d); these kernels are FP64-pipe / latency bound, not HBM bound "
-                             "(DESIGN.md section 5)"},
+                             "(DESIGN.md section 4); fp64 = SURVEY 8(d) algorithmic flops (45 per node visit, 904 visits per "
+                             "particle at this N) against the nominal 37 TFLOP/s FP64 peak",
+                     "fp64": {"gravity_tflops": round(45.0 * 904.0 * (n / world) / (phases["gravity"]["ms"] * 1e-3) / 1e12, 3),
+                              "peak_nominal_tflops": 37.0,
+                              "frac": round(45.0 * 904.0 * (n / world) / (phases["gravity"]["ms"] * 1e-3) / 1e12 / 37.0, 4)}},
         "sph_sums": {"ms": round(sph_ms, 4), "achieved_gbs": round(sph_gbs, 2), "frac": round(sph_gbs / peak, 5),
                      "alg_bytes_per_particle": ALG_BYTES["density"] + ALG_BYTES["force"]},
         "step_alg_bytes": {"per_particle_step": ALG_BYTES_STEP,
