@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(HB) eos_kernel(int64_t N, const double2 *__res
                                                   const double4 *__restrict__ vel4, int poly, double cs, double gamma,
                                                   const unsigned long long *__restrict__ scal,
                                                   double *__restrict__ prr, double *__restrict__ cs_s,
-                                                  double4 *__restrict__ pos4) {
+                                                  double4 *__restrict__ pos4 /* null: pos4.w already holds h */) {
     if (scal[SC_ERR] != 0ull) return;
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
@@ -84,7 +84,18 @@ __global__ void __launch_bounds__(HB) eos_kernel(int64_t N, const double2 *__res
     }
     prr[s] = P / (rho * rho);
     cs_s[s] = c;
-    pos4[s].w = a.x;
+    if (pos4) pos4[s].w = a.x;
+}
+
+// h = r[:, end] ./ 2 (:151) straight from the search result into pos4.w: lets the tree walk start while the density
+// runs on the second stream (single GPU; same expression as density_kernel, so the value is the one it stores in hr)
+__global__ void __launch_bounds__(HB) smoothing_kernel(int64_t N, const double *__restrict__ d2k,
+                                                        const unsigned long long *__restrict__ scal,
+                                                        double4 *__restrict__ pos4) {
+    if (scal[SC_ERR] != 0ull) return;
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    pos4[s].w = sqrt(d2k[s]) / 2;
 }
 
 // Pair loop of hydroCalculation / getAV / evolve_K!.  The target's own update is kept in registers and
@@ -168,11 +179,17 @@ cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1) {
     return cudaGetLastError();
 }
 
-cudaError_t sph_launch_eos(sph_handle *h) {
+cudaError_t sph_launch_eos(sph_handle *h, bool write_h) {
     sph_note(1);
     eos_kernel<<<(int)((h->N + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->hr, h->vel4,
                                                                   h->p.eos == SPH_EOS_POLYTROPIC, h->p.cs, h->p.gamma,
-                                                                  h->scal, h->prr, h->cs_s, h->pos4);
+                                                                  h->scal, h->prr, h->cs_s, write_h ? h->pos4 : nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t sph_launch_smoothing(sph_handle *h) {
+    sph_note(1);
+    smoothing_kernel<<<(int)((h->N + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->d2k, h->scal, h->pos4);
     return cudaGetLastError();
 }
 

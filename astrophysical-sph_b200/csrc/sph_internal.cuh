@@ -191,9 +191,10 @@ struct sph_handle {
     // the force kernel (+ its all-reduce) runs on a second stream, concurrently with the tree walk: both only need
     // the density/EOS results, and the latency-bound force kernel fills the issue slots the walk's tail leaves idle
     cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, fev[2]{};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, fev[2]{}, dev[2]{};   // fev / dev: force and density phases on the stream they ran on
     void *nccl2 = nullptr;  // communicator of stream2 (NCCL calls of one communicator must not run concurrently)
     bool overlap = true;
+    bool density_overlapped = false;   // last evaluation ran density + EOS on stream2 as well (single GPU)
     bool ev_valid = false;
     // multi-GPU
     int nranks = 1, rank = 0;
@@ -239,7 +240,8 @@ cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t 
 
 // ---- hydro.cu ------------------------------------------------------------------------------------
 cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1);
-cudaError_t sph_launch_eos(sph_handle *h);
+cudaError_t sph_launch_eos(sph_handle *h, bool write_h);
+cudaError_t sph_launch_smoothing(sph_handle *h);   // pos4.w = h from the K-th distances (before the density)
 cudaError_t sph_launch_force(sph_handle *h, int64_t t0, int64_t t1);
 
 // ---- gravity.cu ----------------------------------------------------------------------------------

@@ -349,11 +349,11 @@ def test_run_simulation_writes_reference_files(sph, oracle, tmp_path):
 
 
 @pytest.mark.parametrize("env", ["SPH_B200_SORT_CLASSIC", "SPH_B200_COM_LEVELS", "SPH_B200_WALK_BATCH", "SPH_B200_WALK_DFS",
-                                 "SPH_B200_WALK_T", "SPH_B200_NO_OVERLAP", "SPH_B200_KNN_WARP", "SPH_B200_KNN_SORT",
-                                 "SPH_B200_NO_HINT"])
+                                 "SPH_B200_WALK_T", "SPH_B200_NO_OVERLAP", "SPH_B200_DENSITY_OVERLAP", "SPH_B200_KNN_WARP",
+                                 "SPH_B200_KNN_SORT", "SPH_B200_NO_HINT"])
 def test_alternative_paths_agree(sph, env):
     """Every switchable kernel variant (classic sort passes, level-wise COM sweep, batched walk, shared walk without the
-    pair queue, pair queue for single-lane cells only, serial force/walk, warp-per-target search, sorted instead of
+    pair queue, pair queue for single-lane cells only, serial force/walk, density beside the walk, warp-per-target search, sorted instead of
     selected hits, unhinted search) passes the same two-step parity check against the oracle."""
     import subprocess
     import sys
