@@ -21,7 +21,7 @@ namespace {
 
 constexpr int GW_WARPS = 4;
 constexpr int GW_STACK = 192;
-constexpr int GW_REC = SPH_WALK_REC;   // double4 per walk record: {rCOM, Mass | h_j}, {(2L)^2, radius, child info, range}, {lo.xyz, hi.x}, {hi.y, hi.z, ..}
+constexpr int GW_REC = SPH_WALK_REC;   // double4 per walk record: {rCOM, Mass | h_j}, {(2L)^2, radius, child info, range}
 
 // coefficients of the softened kernels below, read as constant-bank operands (as literals each one costs two
 // uniform-register moves in front of the FP64 instruction that uses it)
@@ -76,14 +76,6 @@ __device__ __forceinline__ double axis_dist_bits(double lo, double hi, double p)
     const double a = lo - p, b = p - hi;
     const double bz = __double2hiint(b) >= 0 ? b : 0.0;
     return __double2hiint(a) >= 0 ? a : bz;
-}
-
-__device__ __forceinline__ int2 unpack_i2(double v) {
-    const long long b = __double_as_longlong(v);
-    return make_int2((int)(b & 0xffffffffLL), (int)(b >> 32));
-}
-__device__ __forceinline__ double pack_i2(int x, int y) {
-    return __longlong_as_double((long long)(unsigned)x | ((long long)y << 32));
 }
 
 // Root child handled by block row y of a tile: row 0 takes the child that CONTAINS the tile (its walk is by far the
@@ -271,8 +263,8 @@ __device__ __forceinline__ bool cell_accepted(const SphTree &t, int n, double s_
     if (accept) {
         const double w = radius + h2x;
         if (!(d_sq > w * w)) {
-            const double4 B = t.nodeW[GW_REC * (int64_t)n + 2];
-            const double4 C = t.nodeW[GW_REC * (int64_t)n + 3];
+            const double4 B = t.nodeBC[2 * (int64_t)n];
+            const double4 C = t.nodeBC[2 * (int64_t)n + 1];
             const double ex = axis_dist_bits(B.x, B.w, px), ey = axis_dist_bits(B.y, C.x, py), ez = axis_dist_bits(B.z, C.y, pz);
             accept = quotient_less(hi2, sph_d2_exact(ex, ey, ez), 0.25);
         }
@@ -666,10 +658,6 @@ __global__ void pack_nodes_kernel(SphTree t, const double4 *__restrict__ pos4, c
         double4 *rec = t.nodeW + GW_REC * k;
         rec[0] = A;
         rec[1] = make_double4(D.x, D.y, pack_i2(I.x, I.y), pack_i2(t.nstart[k], t.ncount[k]));
-        if (I.y != 0) {           // cell bounds for the exact evaluation of clause 2, in the same 128-byte line
-            rec[2] = t.nodeB[k];
-            rec[3] = t.nodeC[k];
-        }
     }
 }
 

@@ -428,12 +428,13 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, BLOCKS) knn_quad_kernel(int64_t
                 int2 Ic = make_int2(0, 0);     // the child's own children: fetched with its box, so a pop needs no dependent load
                 if (c8 < nch) {
                     const int c = first + c8;
-                    Ic = t.nodeI[c];
-                    const double4 B = t.nodeB[c];
-                    const double4 C = t.nodeC[c];
+                    const double4 B = t.nodeBC[2 * (int64_t)c];         // {lo.xyz, hi.x}
+                    const double4 C = t.nodeBC[2 * (int64_t)c + 1];     // {hi.y, hi.z, child bits, range bits}
+                    Ic = unpack_i2(C.z);
                     pass = B.x <= bhi[0] && B.w >= blo[0] && B.y <= bhi[1] && C.x >= blo[1] && B.z <= bhi[2] && C.y >= blo[2];
-                    cstart = t.nstart[c];
-                    ccount = t.ncount[c];
+                    const int2 rg = unpack_i2(C.w);
+                    cstart = rg.x;
+                    ccount = rg.y;
                 }
                 const bool is_bucket = ccount <= bucket;
                 const unsigned bm = __ballot_sync(0xffffffffu, pass && is_bucket);

@@ -313,7 +313,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
         if (const char *e = getenv("SPH_B200_NODE_FACTOR")) factor = atof(e) > 1.5 ? atof(e) : 3.0;
         t.cap = (int64_t)(factor * (double)N) + 1024;
         const size_t C = (size_t)t.cap;
-        CK(dalloc(&t.nodeI, C)); CK(dalloc(&t.nodeA, C)); CK(dalloc(&t.nodeB, C)); CK(dalloc(&t.nodeC, C)); CK(dalloc(&t.nodeD, C)); CK(dalloc(&t.nodeW, SPH_WALK_REC * C));
+        CK(dalloc(&t.nodeI, C)); CK(dalloc(&t.nodeA, C)); CK(dalloc(&t.nodeB, C)); CK(dalloc(&t.nodeC, C)); CK(dalloc(&t.nodeD, C)); CK(dalloc(&t.nodeW, SPH_WALK_REC * C)); CK(dalloc(&t.nodeBC, 2 * C));
         CK(dalloc(&t.nstart, C)); CK(dalloc(&t.ncount, C)); CK(dalloc(&t.ndepth, C));
         CK(dalloc(&t.parent, C)); CK(dalloc(&t.arrive, C));
         CK(dalloc(&t.old_start, C)); CK(dalloc(&t.old_depth, C));
@@ -354,7 +354,7 @@ int sph_destroy(sph_handle *h) {
                     h->o_g, h->keys, h->keys_alt, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->prr,
                     h->cs_s, h->d2k, h->nbr, h->s_red, h->walk_buf, h->walk_part, h->cnt,
                     h->base, h->scal, h->stat_dev, h->red_partial, h->tree.nodeI, h->tree.nodeA, h->tree.nodeB,
-                    h->tree.nodeC, h->tree.nodeD, h->tree.nodeW, h->tree.parent, h->tree.arrive, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
+                    h->tree.nodeC, h->tree.nodeD, h->tree.nodeW, h->tree.nodeBC, h->tree.parent, h->tree.arrive, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
                     h->tree.old_depth, h->tree.dkey_in, h->tree.dkey_out, h->tree.dval_in, h->tree.dval_out,
                     h->tree.bfs_of_old, h->tree.level_start};
     for (void *p : ptrs)

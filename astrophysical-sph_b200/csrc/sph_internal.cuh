@@ -18,7 +18,7 @@
 
 #define SPH_LEVELS 21           // octant levels held by one 63-bit key
 #define SPH_MAX_RANKS 16
-#define SPH_WALK_REC 4           // double4 per walk record of the octree (one 128-byte line per node)
+#define SPH_WALK_REC 2           // double4 per walk record of the octree (two nodes per 128-byte line)
 #define SPH_WALK_DEAL 16         // walk tiles (128 targets) are dealt to the ranks in groups of 16 consecutive tiles:
                                  // round-robin balances the load, consecutive tiles keep the tree nodes hot in L2
 
@@ -104,6 +104,15 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return fma(y * e, 1.0 + e, y);                 // y (1 + e + e^2)
 }
 
+// two ints in the bit pattern of a double (node records keep their integer fields next to the FP64 ones)
+__device__ __forceinline__ int2 unpack_i2(double v) {
+    const long long b = __double_as_longlong(v);
+    return make_int2((int)(b & 0xffffffffLL), (int)(b >> 32));
+}
+__device__ __forceinline__ double pack_i2(int x, int y) {
+    return __longlong_as_double((long long)(unsigned)x | ((long long)y << 32));
+}
+
 // Squared distance exactly as NearestNeighbors' Euclidean metric evaluates it in the oracle's
 // restatement: (dx*dx + dy*dy) + dz*dz with every product and sum rounded (never contracted to FMA).
 __device__ __forceinline__ double sph_d2_exact(double dx, double dy, double dz) {
@@ -121,6 +130,7 @@ struct SphTree {
     int2 *nodeI = nullptr;
     double4 *nodeA = nullptr, *nodeB = nullptr, *nodeC = nullptr;
     double4 *nodeW = nullptr;  // walk records, SPH_WALK_REC x double4 per node: {com.xyz, mass | h_j}, {(2L)^2, radius, bits{first|slot, nch|leafmask<<8}, bits{nstart, ncount}}, nodeB, nodeC
+    double4 *nodeBC = nullptr; // compact search / clause-2 record of node k: [2k] {lo.xyz, hi.x}, [2k+1] {hi.y, hi.z, bits{first child | slot, nchild | leafmask << 8}, bits{nstart, ncount}}
     double2 *nodeD = nullptr;  // internal nodes: {(2 Length)^2, upper bound of the distance from rCOM to any point of the cell}
     int *nstart = nullptr, *ncount = nullptr, *ndepth = nullptr;
     int *parent = nullptr, *arrive = nullptr;   // bottom-up COM sweep: parent id, number of finished children

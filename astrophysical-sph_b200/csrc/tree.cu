@@ -160,8 +160,10 @@ __global__ void __launch_bounds__(TB) node_build_kernel(const uint64_t *__restri
         t.nodeB[k] = make_double4(g.lo[0], g.lo[1], g.lo[2], g.hi[0]);
         const double s2 = (g.L * 2) * (g.L * 2);  // s = node.Length*2 ; s^2  (F/gravOctree_Single.jl:257,265)
         t.nodeC[k] = make_double4(g.hi[1], g.hi[2], s2, g.L);
+        int2 I;
         if (leaf) {
-            t.nodeI[k] = make_int2(s, 0);
+            I = make_int2(s, 0);
+            t.nodeI[k] = I;
             const double4 p = pos4[s];
             t.nodeA[k] = make_double4(p.x, p.y, p.z, mass);  // leaf: rCOM = particle, Mass = m (:186-194, :69)
         } else {
@@ -179,10 +181,14 @@ __global__ void __launch_bounds__(TB) node_build_kernel(const uint64_t *__restri
                 lo = nb;
             }
             const int fc = bfs_of_old[o + 1];
-            t.nodeI[k] = make_int2(fc, nch | (leafmask << 8));
+            I = make_int2(fc, nch | (leafmask << 8));
+            t.nodeI[k] = I;
             for (int c = 0; c < nch; ++c) t.parent[fc + c] = (int)k;
             if (k == 0) t.parent[0] = -1;
         }
+        // compact copy for the 4-target search (box + children + range in two adjacent sectors) and the walk's exact clause 2
+        t.nodeBC[2 * k] = make_double4(g.lo[0], g.lo[1], g.lo[2], g.hi[0]);
+        t.nodeBC[2 * k + 1] = make_double4(g.hi[1], g.hi[2], pack_i2(I.x, I.y), pack_i2(s, e - s));
     }
 }
 
