@@ -15,6 +15,8 @@
 // summation order differs (the reference's own order already drifts through its leaf list surgery,
 // :293-300), and 1/d, 1/d^3 come from one rsqrt (<= 4 ulp; the parity bar for gravity is 1e-6).
 // Node data is read with warp-uniform addresses (32 B per double4, broadcast to the warp).
+// walk_pairs_kernel (default) adds a pair queue for the cells only a few lanes still have to open (see its header);
+// walk_kernel is the shared walk alone, walk_batch_kernel a batched variant of it.
 #include "sph_internal.cuh"
 
 namespace {

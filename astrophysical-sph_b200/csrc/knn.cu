@@ -278,16 +278,22 @@ __global__ void point_density_kernel(int64_t M, int K, const double *__restrict_
 // balls) serves all 4 targets, and the particles of the overlapping buckets are first expanded into a dense
 // shared-memory index list so that every test round has 32 busy lanes (buckets hold ~12 particles on average).
 // Each lane tests its candidate against the 4 balls and appends it to the matching buffers by ballot prefix.
-// A target whose ball held >= K particles (and fit its 96-entry buffer) owns its exact K nearest; they are
-// ordered by (d2, particle id) with a register bitonic network over shuffles (<= 64 hits) or a rank sort, and
-// stored straight to their sorted position.  Targets without a usable hint, with < K particles in the ball,
-// an overflowing buffer or tied distances are queued for the warp-per-target kernel, which restarts from the
-// guaranteed radius and breaks ties by particle id: exactness never depends on the hint.
+// A target whose ball held >= K particles (and fit its 96-entry buffer) owns its exact K nearest.  The lists need
+// no order (density / force skip the self entry by index, export_sorted_kernel orders on demand), so the K-th
+// smallest squared distance is SELECTED: starting from the previous evaluation's (2 h_prev)^2 the warp steps over
+// distinct key values and recounts (2-3 steps between two evaluations), then emits the keys <= it in buffer order;
+// the register bitonic network / rank sort remains as the fallback after KQ_SEL_STEPS steps (SPH_B200_KNN_SORT=1:
+// always).  Targets without a usable hint, with < K particles in the ball, an overflowing buffer or a tie AT the
+// K-th distance are queued for the warp-per-target kernel, which restarts from the guaranteed radius and breaks
+// ties by particle id: exactness never depends on the hint.
+// The walk pops up to 4 cells per iteration (lane group g tests the <= 8 children of cell g against the box); the
+// children's {box, child info, particle range} come from the compact nodeBC records the tree build writes, and the
+// stack entries carry {first child, count}, so a pop issues no dependent load.
 // ---------------------------------------------------------------------------------------------------
 constexpr int KQ_T = 4;
 constexpr int KQ_CAP = 96;
 constexpr int KQ_WARPS = 5;
-constexpr int KQ_BLOCKS = 4;     // resident blocks per SM (5 fit, but leave no L1 next to their shared memory: 3.0 vs 2.5 ms)
+constexpr int KQ_BLOCKS = 4;     // resident blocks per SM (the register budget of 5 spills: 3.0 vs 2.5 ms)
 constexpr int KQ_BUCKET = 64;   // largest cell scanned as a range (list sizing); the default threshold is 32 (SPH_B200_KNN_BUCKET)
 constexpr int KQ_BKS = 64;      // buckets gathered before a flush
 constexpr int KQ_CAND = 512;    // candidates gathered before a flush (>= 8 * KQ_BUCKET)
