@@ -10,7 +10,7 @@
 // (DESIGN.md section 4): 1 843 shared iterations serve 901 visits per lane (packing 0.49); independent walks need 975
 // iterations but touch ~20 lines per load instruction; sparse cells are half of the iterations and a seventh of the visits.
 //
-// build / run:  g++ -O2 -o /tmp/walk_sim tools/walk_sim.cpp && /tmp/walk_sim 1000000 12 24 12 [dist: 0 uniform, 1 gaussian]
+// build / run:  g++ -O2 -o /tmp/walk_sim tools/walk_sim.cpp && /tmp/walk_sim 1000000 12 24 12 [dist: 0 uniform, 1 gaussian] [hilbert: 0/1]
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -52,6 +52,26 @@ int main(int argc,char**argv){
     nodes.reserve(2*N); int root=build(all,0,0,0,l);
     { deque<int> q{root}; int k=0; while(!q.empty()){int n=q.front(); q.pop_front(); nodes[n].bfs=k++; for(int c=0;c<nodes[n].nch;++c) q.push_back(nodes[n].child[c]);} }
     vector<int> order; { vector<int> st{root}; while(!st.empty()){int n=st.back(); st.pop_back(); if(nodes[n].part>=0) order.push_back(nodes[n].part); else for(int c=nodes[n].nch-1;c>=0;--c) st.push_back(nodes[n].child[c]);} }
+    if (argc > 6 && atoi(argv[6]) == 1) {
+        // regroup the targets along a 3-D Hilbert curve (10 bits per axis) instead of the tree's Z-order: how much of the
+        // packing loss is due to the jumps of the Z-order?
+        auto hilbert = [&](int i) {
+            unsigned X3[3] = {(unsigned)((X[i] + l) / (2 * l) * 1023.999), (unsigned)((Y[i] + l) / (2 * l) * 1023.999), (unsigned)((Z[i] + l) / (2 * l) * 1023.999)};
+            const int b = 10; unsigned M = 1u << (b - 1), P, Q, t;
+            for (Q = M; Q > 1; Q >>= 1) { P = Q - 1; for (int k = 0; k < 3; ++k) { if (X3[k] & Q) X3[0] ^= P; else { t = (X3[0] ^ X3[k]) & P; X3[0] ^= t; X3[k] ^= t; } } }
+            for (int k = 1; k < 3; ++k) X3[k] ^= X3[k - 1];
+            t = 0; for (Q = M; Q > 1; Q >>= 1) if (X3[2] & Q) t ^= Q - 1;
+            for (int k = 0; k < 3; ++k) X3[k] ^= t;
+            unsigned long long h = 0;
+            for (int bit = b - 1; bit >= 0; --bit) for (int k = 0; k < 3; ++k) h = (h << 1) | ((X3[k] >> bit) & 1u);
+            return h;
+        };
+        vector<pair<unsigned long long,int>> hk(N);
+        for (int s = 0; s < N; ++s) hk[s] = {hilbert(order[s]), order[s]};
+        sort(hk.begin(), hk.end());
+        for (int s = 0; s < N; ++s) order[s] = hk[s].second;
+        printf("targets regrouped in Hilbert order\n");
+    }
     if(dist==1){ // h from local density estimate: crude, use distance to 50th in key order window
         for(int s=0;s<N;++s){int i=order[s]; int a=max(0,s-25), b=min(N-1,s+25); double m=0; for(int t=a;t<=b;++t){int j=order[t]; double d=hypot(hypot(X[i]-X[j],Y[i]-Y[j]),Z[i]-Z[j]); m=max(m,d);} H[i]=0.5*m*0.6;} }
     long dense_visits=0, priv_iters=0, priv_lanevisits=0, lanevisits_dense=0, lines=0, drains=0, maxq=0;
