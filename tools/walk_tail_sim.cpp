@@ -1,9 +1,8 @@
 // walk_tail_sim.cpp -- CPU design study (not on the product path): how a tile's shared-walk iterations distribute over the
 // root's children (the work items of walk_kernel / walk_pairs_kernel, blockIdx.y) and over (root child, grandchild) pairs.
 // N = 1e6 uniform sphere: 1 840 iterations per 32 targets, 80 % of them under the root child that contains the tile,
-// 62 % under one grandchild.  With P ranks a rank owns N/(128 P) long items; at P = 8 they fill 82 % of the resident
-// block slots, so the long phase runs at 82 % of the machine: (0.80 / 0.82 + 0.20) = 1.18x the ideal share, which is what
-// SPH_B200_WALK_FAKE_RANKS=8 measures (1.05 vs 0.77 ms + fixed kernels).  A two-level split would only reach 1.14x.
+// 62 % under one grandchild.  With P ranks a rank owns N/(128 P) long items (977 at P = 8, for 1 184 resident block slots)
+// and 7x as many short ones; SPH_B200_WALK_FAKE_RANKS=8 measures 1.05 ms for the rank's share against 0.77 ms ideal.
 // build / run:  g++ -O2 -o /tmp/walk_tail_sim tools/walk_tail_sim.cpp && /tmp/walk_tail_sim 1000000
 #include <cstdio>
 #include <cstdlib>
