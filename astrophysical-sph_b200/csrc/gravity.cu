@@ -16,7 +16,7 @@
 // :293-300), and 1/d, 1/d^3 come from one rsqrt (<= 4 ulp; the parity bar for gravity is 1e-6).
 // Node data is read with warp-uniform addresses (32 B per double4, broadcast to the warp).
 // walk_pairs_kernel (default) adds a pair queue for the cells only a few lanes still have to open (see its header);
-// walk_kernel is the shared walk alone, walk_batch_kernel a batched variant of it.
+// walk_kernel is the shared walk alone (also used when node ids do not fit the pair encoding).
 #include "sph_internal.cuh"
 
 namespace {
@@ -80,19 +80,18 @@ __device__ __forceinline__ double axis_dist_bits(double lo, double hi, double p)
     return __double2hiint(a) >= 0 ? a : bz;
 }
 
-// Root child handled by block row y of a tile: row 0 takes the child that CONTAINS the tile (its walk is by far the
-// longest: the whole near field), rows 1.. the others in cyclic order.  The hardware starts blocks in grid order, so
-// every long work item begins before any short one and the short ones fill the tail.
-__device__ __forceinline__ int walk_root_child(const double4 *__restrict__ W, int2 R, int64_t first_slot, int y) {
+// Root children handled by block row y of a tile.  The children are ordered o = 0, 1, ..: o = 0 is the child that
+// CONTAINS the tile (its walk is by far the longest: the whole near field), o >= 1 the others in cyclic order; row y of
+// `rows` takes o = y, y + rows, ...  The hardware starts blocks in grid order, so every long work item begins before
+// any short one and the short ones fill the tail.
+__device__ __forceinline__ int walk_root_near(const double4 *__restrict__ W, int2 R, int64_t first_slot) {
     const int nch = R.y & 0xff;
-    if (y >= nch) return -1;
     int near = 0;
     for (int c = 0; c < nch; ++c) {
         const int2 rg = unpack_i2(W[GW_REC * (int64_t)(R.x + c) + 1].w);    // {nstart, ncount}
         if (first_slot >= rg.x && first_slot < (int64_t)rg.x + rg.y) near = c;
     }
-    const int rc = near + y;
-    return rc >= nch ? rc - nch : rc;
+    return near;
 }
 
 template <bool COUNT>
@@ -124,14 +123,23 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int n
     const unsigned amask = __ballot_sync(0xffffffffu, active);
     int sp = 0;
     // the walk starts by opening the root: the root itself is never tested (:246-249).  The root's children are
-    // dealt to blockIdx.y: 8x more, 8x shorter work items (wave quantisation matters when a rank owns ~1 wave of
-    // tiles); the partial sums are added in child order by walk_reduce_kernel, so results stay deterministic.
+    // dealt to the gridDim.y block rows: more, shorter work items (wave quantisation matters when a rank owns ~1 wave
+    // of tiles); the partial sums are added in row order by walk_reduce_kernel, so results stay deterministic.
     const int2 R = unpack_i2(W[1].z);
-    const int rc = walk_root_child(W, R, gtile * (GW_WARPS * 32), blockIdx.y);
-    if (rc < 0) return;
+    const int rnch = R.y & 0xff;
+    const int row = blockIdx.y, rows = gridDim.y;
+    if (row >= rnch) return;
     if (amask) {
-        if (lane == 0) stack[0] = make_int4(R.x + rc, 1 | ((((R.y >> 8) >> rc) & 1) << 8), (int)amask, 0);
-        sp = 1;
+        const int near = walk_root_near(W, R, gtile * (GW_WARPS * 32));
+        if (lane == 0) {
+            int o = row;
+            while (o + rows < rnch) o += rows;
+            for (; o >= 0; o -= rows) {               // pushed far to near: the near child is walked first
+                const int rc = near + o >= rnch ? near + o - rnch : near + o;
+                stack[sp++] = make_int4(R.x + rc, 1 | ((((R.y >> 8) >> rc) & 1) << 8), (int)amask, 0);
+            }
+        }
+        sp = __shfl_sync(0xffffffffu, sp, 0);
     }
     __syncwarp();
     while (sp > 0) {
@@ -209,9 +217,9 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int n
         __syncwarp();
     }
     if (active) {
-        double *out = part + (size_t)rc * 4 * chunk;
+        double *out = part + (size_t)row * 4 * chunk;
         out[local] = gx; out[local + chunk] = gy; out[local + 2 * chunk] = gz;
-        out[local + 3 * chunk] = rc == 0 ? ph - (m * (7.0 / 5) / hi) : ph;        // (:303), once
+        out[local + 3 * chunk] = row == 0 ? ph - (m * (7.0 / 5) / hi) : ph;       // (:303), once
     }
     if (COUNT) {
 #pragma unroll
@@ -313,15 +321,24 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N,
     double gx = 0.0, gy = 0.0, gz = 0.0, ph = 0.0;
     unsigned long long visits = 0;
     const unsigned amask = __ballot_sync(0xffffffffu, active);
-    // the root is opened unconditionally (:246-249); its children are dealt to blockIdx.y (see walk_kernel)
+    // the root is opened unconditionally (:246-249); its children are dealt to the block rows (see walk_kernel)
     const int2 R = unpack_i2(W[1].z);
-    const int rc = walk_root_child(W, R, gtile * (GW_WARPS * 32), blockIdx.y);
-    if (rc < 0) return;
+    const int rnch = R.y & 0xff;
+    const int row = blockIdx.y, rows = gridDim.y;
+    if (row >= rnch) return;
     sm.acc[lane] = make_double4(0.0, 0.0, 0.0, 0.0);
     int sp = 0, qn = 0;
     if (amask) {
-        if (lane == 0) sm.stack[0] = make_int2((R.x + rc) | (1 << 27), (int)amask);
-        sp = 1;
+        const int near = walk_root_near(W, R, gtile * (GW_WARPS * 32));
+        if (lane == 0) {
+            int o = row;
+            while (o + rows < rnch) o += rows;
+            for (; o >= 0; o -= rows) {               // pushed far to near: the near child is walked first
+                const int rc = near + o >= rnch ? near + o - rnch : near + o;
+                sm.stack[sp++] = make_int2((R.x + rc) | (1 << 27), (int)amask);
+            }
+        }
+        sp = __shfl_sync(0xffffffffu, sp, 0);
     }
     __syncwarp();
     for (;;) {
@@ -461,9 +478,9 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N,
     if (active) {
         const double4 a = sm.acc[lane];
         gx += a.x; gy += a.y; gz += a.z; ph += a.w;
-        double *out = part + (size_t)rc * 4 * chunk;
+        double *out = part + (size_t)row * 4 * chunk;
         out[local] = gx; out[local + chunk] = gy; out[local + 2 * chunk] = gz;
-        out[local + 3 * chunk] = rc == 0 ? ph - (m * (7.0 / 5) / hi) : ph;        // (:303), once
+        out[local + 3 * chunk] = row == 0 ? ph - (m * (7.0 / 5) / hi) : ph;       // (:303), once
     }
     if (COUNT) {
 #pragma unroll
@@ -472,177 +489,16 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N,
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Batched walk (opt-in: SPH_B200_WALK_BATCH=1).  Same decisions and the same per-lane arithmetic as walk_kernel above, but the
-// warp pops up to 32 cells per round: lane k fetches the 64-byte record of cell k (coalesced-ish: siblings
-// are contiguous) and parks it in shared memory; then every lane - one target each - runs over the parked
-// cells reading them with broadcast shared-memory loads.  The inner loop has no global loads, no stack
-// traffic and no votes; the lanes that must open cell k are collected afterwards with one vote per cell,
-// and the owners of opened cells push the children (exclusive scan for the stack slots).
-// The batch size adapts so that the shared-memory stack can never overflow (B <= (CAP - sp) / 7; B = 1 is
-// the depth-first walk whose depth is bounded by 7 * 21 + 8 entries).
-// ---------------------------------------------------------------------------------------------------
-constexpr int GB_WARPS = 4;
-constexpr int GB_CAP = 768;      // stack entries per warp
-
-struct GbWarp {
-    double4 recA[32];            // {rCOM, Mass | h_j}
-    double4 recV[32];            // {(2L)^2, radius, child info, range}
-    int2 ent[32];                // {cell id | leaf << 31, lane mask}
-    int2 stack[GB_CAP + 160];   // + the depth-first excursion of the B = 1 regime
-};
-
-template <bool COUNT>
-__global__ void __launch_bounds__(GB_WARPS * 32, 4) walk_batch_kernel(int64_t N, int nranks, int rank, int64_t chunk,
-                                                                      const double4 *__restrict__ pos4, SphTree t,
-                                                                      double theta_sq, double th_lo, double th_hi, double m,
-                                                                      unsigned long long *__restrict__ scal,
-                                                                      double *__restrict__ part /* [8][4][chunk] */) {
-    extern __shared__ __align__(16) unsigned char gb_smem_raw[];
-    if (scal[SC_ERR] != 0ull) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    GbWarp &sm = reinterpret_cast<GbWarp *>(gb_smem_raw)[warp];
-    const double4 *__restrict__ W = t.nodeW;
-    const int64_t local = (int64_t)blockIdx.x * (GB_WARPS * 32) + threadIdx.x;
-    const int64_t gtile = ((int64_t)(blockIdx.x / SPH_WALK_DEAL) * nranks + rank) * SPH_WALK_DEAL + blockIdx.x % SPH_WALK_DEAL;
-    const int64_t s = gtile * (GB_WARPS * 32) + threadIdx.x;
-    const bool active = s < N;
-    double px = 0, py = 0, pz = 0, hi = 1.0;
-    if (active) {
-        const double4 p = pos4[s];  // .w = h_i
-        px = p.x; py = p.y; pz = p.z; hi = p.w;
-    }
-    const double hi2 = hi * hi;
-    const double h2x = 2.0 * hi * (1.0 + 1e-9);      // clause 2 is certainly true when mindist > h2x
-    double gx = 0.0, gy = 0.0, gz = 0.0, ph = 0.0;
-    unsigned long long visits = 0;
-    const unsigned amask = __ballot_sync(0xffffffffu, active);
-    // the root is opened unconditionally (:246-249); its children are dealt to blockIdx.y (see walk_kernel)
-    const int2 R = unpack_i2(W[1].z);
-    const int rc = walk_root_child(W, R, gtile * (GB_WARPS * 32), blockIdx.y);
-    if (rc < 0) return;
-    int sp = 0;
-    if (amask) {
-        if (lane == 0) sm.stack[0] = make_int2((R.x + rc) | (int)((((unsigned)(R.y >> 8) >> rc) & 1u) << 31), (int)amask);
-        sp = 1;
-    }
-    __syncwarp();
-    while (sp > 0) {
-        // ---- pop a batch
-        int B = (GB_CAP - sp) / 7;
-        B = B < 1 ? 1 : (B > 32 ? 32 : B);
-        B = B < sp ? B : sp;
-        sp -= B;
-        int2 e = make_int2(0, 0);
-        double4 A = make_double4(0, 0, 0, 0), V = A;
-        if (lane < B) {
-            e = sm.stack[sp + lane];
-            const int64_t n = e.x & 0x7fffffff;
-            A = W[GW_REC * n];
-            V = W[GW_REC * n + 1];
-            sm.recA[lane] = A; sm.recV[lane] = V; sm.ent[lane] = e;
-        }
-        __syncwarp();
-        // ---- every lane (target) visits the parked cells
-        unsigned openbits = 0;
-#pragma unroll 2
-        for (int k = 0; k < B; ++k) {
-            const int2 ek = sm.ent[k];
-            if (!((((unsigned)ek.y) >> lane) & 1u)) continue;
-            const double4 Ak = sm.recA[k];
-            const double dx = px - Ak.x, dy = py - Ak.y, dz = pz - Ak.z;   // p_i - rCOM (:255)
-            const double d_sq = sph_d2_exact(dx, dy, dz);                   // (:256)
-            if (COUNT) ++visits;
-            if (ek.x < 0) {
-                // leaf = one particle j; A.w carries h_j, its mass is m; the target's own leaf is skipped (:293-294)
-                const double4 Vk = sm.recV[k];
-                if ((int64_t)unpack_i2(Vk.z).x != s) {
-                    const double h_ij = (hi + Ak.w) / 2;                    // (:259)
-                    double gP, pot;
-                    if (d_sq > 4.0 * (h_ij * h_ij)) {                       // q > 2: Newtonian (:19-20)
-                        const double rinv = fast_rsqrt(d_sq);
-                        gP = rinv * rinv * rinv;
-                        pot = -rinv;
-                    } else {
-                        grav_pair(d_sq, h_ij, gP, pot);
-                    }
-                    const double mg = m * gP;
-                    gx += mg * dx; gy += mg * dy; gz += mg * dz;            // (:263)
-                    ph += m * pot;                                          // (:264)
-                }
-            } else {
-                const double4 Vk = sm.recV[k];
-                // clause 1: s*s/d_sq < theta_sq                                             (:265)
-                bool accept;
-                if (Vk.x < d_sq * th_lo) accept = true;
-                else if (Vk.x > d_sq * th_hi) accept = false;
-                else accept = Vk.x / d_sq < theta_sq;
-                // clause 2: h_i*h_i / mind2 < 0.25, proven from d > radius + 2 h_i, else the reference's expression
-                if (accept) {
-                    const double w = Vk.y + h2x;
-                    if (!(d_sq > w * w)) {
-                        const int n = ek.x;
-                        const double4 Bb = t.nodeB[n];
-                        const double4 Cc = t.nodeC[n];
-                        const double ex = axis_dist(Bb.x, Bb.w, px), ey = axis_dist(Bb.y, Cc.x, py),
-                                     ez = axis_dist(Bb.z, Cc.y, pz);
-                        accept = quotient_less(hi2, sph_d2_exact(ex, ey, ez), 0.25);
-                    }
-                }
-                if (accept) {
-                    const double rinv = fast_rsqrt(d_sq);
-                    const double f = Ak.w * (rinv * rinv * rinv);           // Mass / d^3  (:266-268)
-                    gx += f * dx; gy += f * dy; gz += f * dz;
-                    ph -= Ak.w * rinv;                                      // -Mass / d   (:269)
-                } else {
-                    openbits |= 1u << k;
-                }
-            }
-        }
-        // ---- who opens what: lane k learns the lanes that must descend into its cell
-        unsigned mymask = 0;
-        for (int k = 0; k < B; ++k) {
-            const unsigned mk = __ballot_sync(0xffffffffu, (openbits >> k) & 1u);
-            if (lane == k) mymask = mk;
-        }
-        // ---- owners of opened cells push the children
-        const int2 ci = unpack_i2(V.z);                     // {first child, nch | leafmask << 8} of this lane's cell
-        const int nch = (lane < B && mymask) ? (ci.y & 0xff) : 0;
-        int off = nch;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int a = __shfl_up_sync(0xffffffffu, off, o);
-            if (lane >= o) off += a;
-        }
-        const int total = __shfl_sync(0xffffffffu, off, 31);
-        off -= nch;
-        for (int c = 0; c < nch; ++c)
-            sm.stack[sp + off + c] = make_int2((ci.x + c) | (int)((((unsigned)(ci.y >> 8) >> c) & 1u) << 31), (int)mymask);
-        sp += total;
-        __syncwarp();
-    }
-    if (active) {
-        double *out = part + (size_t)rc * 4 * chunk;
-        out[local] = gx; out[local + chunk] = gy; out[local + 2 * chunk] = gz;
-        out[local + 3 * chunk] = rc == 0 ? ph - (m * (7.0 / 5) / hi) : ph;        // (:303), once
-    }
-    if (COUNT) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
-        if (lane == 0) atomicAdd(scal + SC_VISITS, visits);
-    }
-    (void)lt;
-}
-
-// sum of the per-root-child partial results in child order -> this rank's section of walk_buf
-__global__ void walk_reduce_kernel(int64_t n4 /* 4 * chunk */, const double *__restrict__ part, const double4 *__restrict__ W,
-                                   const unsigned long long *__restrict__ scal, double *__restrict__ out) {
+// sum of the per-row partial results in row order -> this rank's section of walk_buf
+__global__ void walk_reduce_kernel(int64_t n4 /* 4 * chunk */, int rows, const double *__restrict__ part,
+                                   const double4 *__restrict__ W, const unsigned long long *__restrict__ scal,
+                                   double *__restrict__ out) {
     if (scal[SC_ERR] != 0ull) return;
     const int nch = unpack_i2(W[1].z).y & 0xff;
+    const int nr = rows < nch ? rows : nch;          // rows beyond the root's child count wrote nothing
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         double s = 0.0;
-        for (int c = 0; c < nch; ++c) s += part[(size_t)c * n4 + i];
+        for (int c = 0; c < nr; ++c) s += part[(size_t)c * n4 + i];
         out[i] = s;
     }
 }
@@ -667,24 +523,30 @@ __global__ void pack_nodes_kernel(SphTree t, const double4 *__restrict__ pos4, c
 
 cudaError_t sph_launch_walk(sph_handle *h) {
     static_assert(GW_WARPS * 32 == 128, "walk tiles are 128 targets (finish_kernel and sph_comm_init assume it)");
-    sph_note(2);
+    sph_note(1);
     pack_nodes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->tree, h->pos4, h->scal);
     const int64_t tiles = (h->N + 127) / 128;
     const int64_t groups = (tiles + SPH_WALK_DEAL - 1) / SPH_WALK_DEAL;
-    // SPH_B200_WALK_FAKE_RANKS=P (timing experiments on one GPU only): walk the share rank 0 would own among P ranks;
-    // the other targets keep stale results
-    static const int fake_ranks = getenv("SPH_B200_WALK_FAKE_RANKS") ? atoi(getenv("SPH_B200_WALK_FAKE_RANKS")) : 0;
-    const int w_nranks = fake_ranks > 0 && h->nranks == 1 ? fake_ranks : h->nranks;
-    const int w_rank = h->rank;
-    const int64_t blocks = (groups - w_rank + w_nranks - 1) / w_nranks * SPH_WALK_DEAL;   // groups rank, rank + P, ...
-    if (blocks <= 0) return cudaGetLastError();
+    const int64_t blocks = (groups - h->rank + h->nranks - 1) / h->nranks * SPH_WALK_DEAL;   // groups rank, rank + P, ...
+    if (blocks <= 0) {
+        cudaEventRecord(h->wev[0], h->stream);
+        cudaEventRecord(h->wev[1], h->stream);
+        return cudaGetLastError();
+    }
     const double th2 = h->p.theta * h->p.theta;
     double *out = h->walk_buf + (size_t)h->rank * 4 * h->walk_chunk;
-    const dim3 grid((unsigned)blocks, 8);
+    // block rows = work items per tile (the root's children are dealt to them).  One GPU: 2 rows (the child that
+    // contains the tile | the 7 others); several ranks: 8 (a rank then owns about one wave of tiles).  SPH_B200_WALK_ROWS
+    // overrides (1..8).  With one row the kernel writes its sums straight into walk_buf.
+    static const int rows_env = getenv("SPH_B200_WALK_ROWS") ? atoi(getenv("SPH_B200_WALK_ROWS")) : 0;
+    int rows = rows_env > 0 ? rows_env : (h->nranks > 1 ? 8 : 2);
+    rows = rows < 1 ? 1 : (rows > 8 ? 8 : rows);
+    double *part = rows == 1 ? out : h->walk_part;
+    const dim3 grid((unsigned)blocks, (unsigned)rows);
     sph_note(1);
-    static const bool count = getenv("SPH_B200_COUNT_VISITS") != nullptr;
-    // the batched walk (walk_batch_kernel) measures the same as the depth-first walk; it stays opt-in
-    static const bool dfs = getenv("SPH_B200_WALK_BATCH") == nullptr;
+    cudaEventRecord(h->wev[0], h->stream);
+    static const bool count_env = getenv("SPH_B200_COUNT_VISITS") != nullptr;
+    const bool count = count_env || (h->p.flags & SPH_FLAG_COUNT_VISITS) != 0;
     static const bool shared_only = getenv("SPH_B200_WALK_DFS") != nullptr;
     // cells with <= sparse_t interested lanes are evaluated pair-wise (walk_pairs_kernel); 0 = never
     static const int sparse_t = [] {
@@ -692,47 +554,26 @@ cudaError_t sph_launch_walk(sph_handle *h) {
         const int v = e ? atoi(e) : 12;
         return v < 0 ? 0 : (v > GP_TMAX ? GP_TMAX : v);
     }();
-    if (!dfs) {
-        static bool attr_set = false;
-        const size_t smem = sizeof(GbWarp) * GB_WARPS;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(walk_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(walk_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
-        const double lo = th2 * (1.0 - 1e-15), hi = th2 * (1.0 + 1e-15);
-        if (count)
-            walk_batch_kernel<true><<<grid, GB_WARPS * 32, smem, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4,
-                                                                              h->tree, th2, lo, hi, h->p.m, h->scal, h->walk_part);
-        else
-            walk_batch_kernel<false><<<grid, GB_WARPS * 32, smem, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4,
-                                                                               h->tree, th2, lo, hi, h->p.m, h->scal, h->walk_part);
-    } else if (shared_only || h->tree.cap >= (1ll << 27) || h->N >= (1ll << 31)) {
+    if (shared_only || h->tree.cap >= (1ll << 27) || h->N >= (1ll << 31)) {
         // the shared depth-first walk alone (SPH_B200_WALK_DFS=1, or node ids that do not fit the pair encoding)
         if (count)
-            walk_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4, h->tree,
-                                                                     th2, h->p.m, h->scal, h->walk_part);
+            walk_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+                                                                     th2, h->p.m, h->scal, part);
         else
-            walk_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4, h->tree,
-                                                                      th2, h->p.m, h->scal, h->walk_part);
+            walk_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+                                                                      th2, h->p.m, h->scal, part);
     } else {
-        static const bool carve_set = [] {   // experiment: shared-memory carve-out (percent of the maximum) of the pair walk
-            const char *e = getenv("SPH_B200_WALK_CARVE");
-            if (e) {
-                cudaFuncSetAttribute(walk_pairs_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
-                cudaFuncSetAttribute(walk_pairs_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
-            }
-            return true;
-        }();
-        (void)carve_set;
         if (count)
-        walk_pairs_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4, h->tree,
-                                                                       th2, th2 * (1.0 - 1e-15), th2 * (1.0 + 1e-15), h->p.m, sparse_t, h->scal, h->walk_part);
-    else
-        walk_pairs_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, w_nranks, w_rank, h->walk_chunk, h->pos4, h->tree,
-                                                                        th2, th2 * (1.0 - 1e-15), th2 * (1.0 + 1e-15), h->p.m, sparse_t, h->scal, h->walk_part);
+            walk_pairs_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+                                                                           th2, th2 * (1.0 - 1e-15), th2 * (1.0 + 1e-15), h->p.m, sparse_t, h->scal, part);
+        else
+            walk_pairs_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+                                                                            th2, th2 * (1.0 - 1e-15), th2 * (1.0 + 1e-15), h->p.m, sparse_t, h->scal, part);
     }
-    walk_reduce_kernel<<<148 * 8, 256, 0, h->stream>>>(4 * h->walk_chunk, h->walk_part, h->tree.nodeW, h->scal, out);
+    cudaEventRecord(h->wev[1], h->stream);
+    if (rows > 1) {
+        sph_note(1);
+        walk_reduce_kernel<<<148 * 8, 256, 0, h->stream>>>(4 * h->walk_chunk, rows, h->walk_part, h->tree.nodeW, h->scal, out);
+    }
     return cudaGetLastError();
 }

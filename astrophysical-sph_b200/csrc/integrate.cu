@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(IB) dt_kernel(int64_t N, int64_t NS, const dou
                                                  const double *__restrict__ csv, double G, double m, double alpha, double beta,
                                                  unsigned long long *__restrict__ scal) {
     double best = __longlong_as_double(0x7ff0000000000000LL);
+    bool bad = false;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
         const double4 v = vel4[s];
         const double *w = walk_slot(walk_buf, nranks, wchunk, s);
@@ -108,13 +109,19 @@ __global__ void __launch_bounds__(IB) dt_kernel(int64_t N, int64_t NS, const dou
         const double c3 = sqrt(h / a_r);
         const double c4 = h / __dadd_rn(c, __dmul_rn(1.2, __dadd_rn(__dmul_rn(alpha, c), __dmul_rn(beta, s_red[s + 5 * NS]))));
         best = fmin(best, fmin(fmin(c1, c2), fmin(c3, c4)));
+        // fmin drops NaNs, the reference's minimum() propagates them (a blown-up state ends its loop): remember them
+        bad |= (c1 != c1) | (c2 != c2) | (c3 != c3) | (c4 != c4);
     }
     best = block_min(best);
     if (threadIdx.x == 0) atomicMin(&scal[SC_DT], (unsigned long long)__double_as_longlong(best));
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&scal[SC_ERR], (unsigned long long)ERRF_NAN);
 }
 
-__global__ void dt_final_kernel(const unsigned long long *__restrict__ scal, double *__restrict__ dv) {
-    dv[DV_DT] = 0.3 * __longlong_as_double((long long)scal[SC_DT]);
+__global__ void dt_final_kernel(unsigned long long *__restrict__ scal, double *__restrict__ dv) {
+    const double dt = 0.3 * __longlong_as_double((long long)scal[SC_DT]);
+    const bool nan = (scal[SC_ERR] & (unsigned long long)ERRF_NAN) != 0ull;
+    dv[DV_DT] = nan ? __longlong_as_double(0x7ff8000000000000LL) : dt;
+    if (nan) scal[SC_STICKY] |= (unsigned long long)ERRF_NAN;    // survives the reset at the next evaluation's start
 }
 
 // deterministic two-stage sum of NV values per particle

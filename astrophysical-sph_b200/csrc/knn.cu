@@ -638,30 +638,19 @@ cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1) {
     // radius hint: h of the previous evaluation (caller's particle order), valid once one evaluation completed
     const double *hint = (h->hint_valid && !h->no_hint) ? h->o_h : nullptr;
     double fac2 = 1.1 * 1.1;
-    static const double quad_fac = getenv("SPH_B200_KNN_FAC") ? atof(getenv("SPH_B200_KNN_FAC")) : 1.06;
-    static const bool quad_off = getenv("SPH_B200_KNN_WARP") != nullptr;
-    if (hint && h->K <= 64 && !quad_off) {
+    if (hint && h->K <= 64) {
         // 4 targets per warp for the hinted targets, then the warp-per-target search for whatever it queued
         sph_note(2);
+        const double quad_fac = 1.06;      // trial radius = 1.06 x 2 h_prev (measured optimum of 1.03 .. 1.15 at N = 1e6)
         fac2 = quad_fac * quad_fac;
         const int64_t quads = (t1 - t0 + KQ_T - 1) / KQ_T;
         int64_t blocks = (quads + KQ_WARPS - 1) / KQ_WARPS;
         if (blocks > 148 * 5 * 8) blocks = 148 * 5 * 8;
         // SPH_B200_KNN_SORT=1: always order the hits with the sort network instead of selecting the K-th distance
         static const int sel_steps = getenv("SPH_B200_KNN_SORT") ? 0 : KQ_SEL_STEPS;
-        // cells up to this many particles are scanned as ranges (<= KQ_BUCKET: the lists are sized for 8 such cells)
-        static const int bucket = [] {
-            const char *e = getenv("SPH_B200_KNN_BUCKET");
-            const int v = e ? atoi(e) : 32;
-            return v < 1 ? 1 : (v > KQ_BUCKET ? KQ_BUCKET : v);
-        }();
-        static const bool five = getenv("SPH_B200_KNN_BLOCKS5") != nullptr;   // experiment: 5 resident blocks, 80 registers
-        if (five)
-            knn_quad_kernel<5><<<(int)blocks, KQ_WARPS * 32, 0, h->stream>>>(h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2,
-                                                                            sel_steps, bucket, h->scal, h->cnt, h->nbr, h->d2k);
-        else
-            knn_quad_kernel<KQ_BLOCKS><<<(int)blocks, KQ_WARPS * 32, 0, h->stream>>>(h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2,
-                                                                                    sel_steps, bucket, h->scal, h->cnt, h->nbr, h->d2k);
+        const int bucket = 32;             // cells up to this many particles are scanned as ranges (<= KQ_BUCKET)
+        knn_quad_kernel<KQ_BLOCKS><<<(int)blocks, KQ_WARPS * 32, 0, h->stream>>>(h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2,
+                                                                                sel_steps, bucket, h->scal, h->cnt, h->nbr, h->d2k);
         // queued targets keep their own hinted ball (only the shared box was too wide); a failing hint falls back to
         // the guaranteed radius inside the kernel
         knn_kernel<128, true><<<148 * 5, KNN_WARPS * 32, 0, h->stream>>>(
@@ -690,13 +679,10 @@ cudaError_t sph_launch_export_neighbors(sph_handle *h, int *idx_out_dev, double 
     return cudaGetLastError();
 }
 
-// pts_dev: M x 3 column-major device points
-cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t M, double *rho_out_dev) {
+// pts_dev: M x 3 column-major device points; d2s: M x K scratch for the sorted squared distances
+cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t M, double *d2s, double *rho_out_dev) {
     if (M <= 0) return cudaSuccess;
     sph_note(2);
-    double *d2s = nullptr;
-    cudaError_t e = cudaMallocAsync((void **)&d2s, (size_t)M * h->K * sizeof(double), h->stream);
-    if (e != cudaSuccess) return e;
     const int blocks = knn_blocks(M);
     if (h->K <= 96)
         knn_kernel<128, false><<<blocks, KNN_WARPS * 32, 0, h->stream>>>(
@@ -706,7 +692,5 @@ cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t 
             h->N, h->K, 0, M, h->pos4, pts_dev, M, h->perm, h->tree, nullptr, 1.0, nullptr, h->scal, nullptr, nullptr, d2s);
     point_density_kernel<<<(int)((M + 127) / 128), 128, 0, h->stream>>>(M, h->K, d2s, h->p.m,
                                                                          h->p.eos == SPH_EOS_POLYTROPIC, rho_out_dev);
-    e = cudaGetLastError();
-    cudaFreeAsync(d2s, h->stream);
-    return e;
+    return cudaGetLastError();
 }

@@ -6,11 +6,9 @@
 // NearestNeighbors.jl (F/isothermal_hydroKDTree.jl:128): one sort by 63-bit octant path key orders the
 // particles so that EVERY octree cell of every level is a contiguous range.
 //
-// Default: one-sweep passes (8 bits per pass, tile = 256 threads x 8 keys): one histogram kernel for all passes, then
+// One-sweep passes (8 bits per pass, tile = 256 threads x 8 keys): one histogram kernel for all passes, then
 // ONE kernel per pass that ranks its tile with __match_any_sync + per-warp digit counters, learns the digits of the
 // preceding tiles by decoupled look-back and scatters.  HBM traffic per pass: 1 read + 1 write of 12 B per element.
-// Classic three-kernel passes (hist / scan / scatter over ghist[digit][tile]) stay selectable with
-// SPH_B200_SORT_CLASSIC=1 and share the ranking code.
 #include <cstdlib>
 
 #include "sph_internal.cuh"
@@ -20,8 +18,6 @@ namespace {
 constexpr int RS_BITS = 8;
 constexpr int RS_BINS = 1 << RS_BITS;
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 4;     // 1024-key tiles: ~1000 blocks at N = 1e6 keep all SMs busy (16 items ran at 1.6 blocks per SM)
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 constexpr int RS_WARPS = RS_THREADS / 32;
 
 constexpr int SC_THREADS = 512;
@@ -30,82 +26,6 @@ constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
 
 __device__ __forceinline__ int64_t eff_n(int64_t n, const unsigned long long *n_dev) {
     return n_dev ? min((int64_t)*n_dev, n) : n;
-}
-
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n_cap,
-                                                              const unsigned long long *n_dev, int shift,
-                                                              int *__restrict__ ghist, int ntiles) {
-    __shared__ int hist[RS_BINS];
-    const int64_t n = eff_n(n_cap, n_dev);
-    hist[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
-#pragma unroll
-    for (int it = 0; it < RS_ITEMS; ++it) {
-        const int64_t e = base + it * RS_THREADS + threadIdx.x;
-        if (e < n) atomicAdd(&hist[(int)((keys[e] >> shift) & (RS_BINS - 1))], 1);
-    }
-    __syncthreads();
-    ghist[(int64_t)threadIdx.x * ntiles + blockIdx.x] = hist[threadIdx.x];
-}
-
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *__restrict__ keys_in,
-                                                                 const int *__restrict__ vals_in,
-                                                                 uint64_t *__restrict__ keys_out,
-                                                                 int *__restrict__ vals_out, int64_t n_cap,
-                                                                 const unsigned long long *n_dev, int shift,
-                                                                 const int *__restrict__ goff, int ntiles) {
-    __shared__ int cnt[RS_WARPS][RS_BINS];
-    const int64_t n = eff_n(n_cap, n_dev);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
-    __syncthreads();
-
-    // warp w owns the contiguous slice [base + w*512, base + (w+1)*512), visited in 16 rounds of 32
-    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_ITEMS);
-    uint64_t key[RS_ITEMS];
-    int rank[RS_ITEMS];
-    const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int it = 0; it < RS_ITEMS; ++it) {
-        const int64_t e = wbase + it * 32 + lane;
-        const bool ok = e < n;
-        key[it] = ok ? keys_in[e] : 0ull;
-        // invalid lanes get a private pseudo-digit so they never join a valid group
-        const unsigned dig = ok ? (unsigned)((key[it] >> shift) & (RS_BINS - 1)) : (0x10000u + lane);
-        const unsigned grp = __match_any_sync(0xffffffffu, dig);
-        const int leader = __ffs(grp) - 1;
-        int pre = 0;
-        if (ok && lane == leader) {
-            pre = cnt[warp][dig];
-            cnt[warp][dig] = pre + __popc(grp);
-        }
-        pre = __shfl_sync(0xffffffffu, pre, leader);
-        rank[it] = pre + __popc(grp & lt);
-        __syncwarp();
-    }
-    __syncthreads();
-    {   // thread d: turn the per-warp counts of digit d into start offsets (global base + earlier warps)
-        const int d = threadIdx.x;
-        int run = goff[(int64_t)d * ntiles + blockIdx.x];
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            const int c = cnt[w][d];
-            cnt[w][d] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < RS_ITEMS; ++it) {
-        const int64_t e = wbase + it * 32 + lane;
-        if (e < n) {
-            const unsigned dig = (unsigned)((key[it] >> shift) & (RS_BINS - 1));
-            const int dst = cnt[warp][dig] + rank[it];
-            keys_out[dst] = key[it];
-            vals_out[dst] = vals_in[e];
-        }
-    }
 }
 
 // ---------------------------------------------------------------- one-sweep passes
@@ -323,19 +243,11 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 }  // namespace
 
-static size_t classic_temp_bytes(int64_t n) {
-    const int64_t ntiles = cdiv(n, RS_TILE);
-    const int64_t hist = (int64_t)RS_BINS * ntiles;
-    const int64_t scan_tiles_hist = cdiv(hist, SC_TILE);
-    const int64_t scan_tiles_n = cdiv(n + 1, SC_TILE);
-    const int64_t st = scan_tiles_hist > scan_tiles_n ? scan_tiles_hist : scan_tiles_n;
-    return align256((size_t)(hist + 1) * 4) * 2 + align256((size_t)(st + 2) * 4) + 1024;
-}
 static size_t onesweep_temp_bytes(int64_t n) {   // [8][256] counts, [8] tile counters, [8][ntiles][256] status words
     return align256((size_t)(8 * RS_BINS + 8) * 4) + (size_t)8 * cdiv(n, OS_TILE) * RS_BINS * 4 + 1024;
 }
 size_t sph_sort_temp_bytes(int64_t n) {
-    const size_t a = classic_temp_bytes(n), b = onesweep_temp_bytes(n);
+    const size_t a = align256((size_t)(cdiv(n + 1, SC_TILE) + 2) * 4) + 1024, b = onesweep_temp_bytes(n);   // scan | sort
     return a > b ? a : b;
 }
 
@@ -355,55 +267,23 @@ cudaError_t sph_sort_pairs(uint64_t *keys_in, int *vals_in, uint64_t *keys_out, 
                            size_t temp_bytes, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     if (temp_bytes < sph_sort_temp_bytes(n)) return cudaErrorInvalidValue;
-    static const bool classic = getenv("SPH_B200_SORT_CLASSIC") != nullptr;
-    if (!classic) {
-        const int npass = (end_bit - begin_bit + RS_BITS - 1) / RS_BITS;
-        if (npass > 8) return cudaErrorInvalidValue;
-        const int ntiles = (int)cdiv(n, OS_TILE);
-        unsigned *ghist = (unsigned *)temp;
-        unsigned *counters = ghist + 8 * RS_BINS;
-        unsigned *status = (unsigned *)((char *)temp + align256((size_t)(8 * RS_BINS + 8) * 4));
-        cudaMemsetAsync(temp, 0, align256((size_t)(8 * RS_BINS + 8) * 4) + (size_t)npass * ntiles * RS_BINS * 4, st);
-        sph_note(2 + npass);
-        int hb = (int)cdiv(n, RS_THREADS * 16);
-        hb = hb < 1 ? 1 : (hb > 148 * 8 ? 148 * 8 : hb);
-        os_hist_kernel<<<hb, RS_THREADS, 0, st>>>(keys_in, n, n_dev, begin_bit, npass, ghist);
-        os_prefix_kernel<<<1, RS_THREADS, 0, st>>>(ghist, npass);
-        uint64_t *ka = keys_in, *kb = keys_out;
-        int *va = vals_in, *vb = vals_out;
-        for (int p = 0; p < npass; ++p) {
-            os_pass_kernel<<<ntiles, RS_THREADS, 0, st>>>(ka, va, kb, vb, n, n_dev, begin_bit + p * RS_BITS, ghist + p * RS_BINS,
-                                                          status + (size_t)p * ntiles * RS_BINS, counters + p);
-            uint64_t *tk = ka; ka = kb; kb = tk;
-            int *tv = va; va = vb; vb = tv;
-        }
-        if (ka != keys_out) {  // result currently in keys_in/vals_in
-            cudaMemcpyAsync(keys_out, ka, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
-            cudaMemcpyAsync(vals_out, va, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
-        }
-        return cudaGetLastError();
-    }
-    const int ntiles = (int)cdiv(n, RS_TILE);
-    const int64_t hist = (int64_t)RS_BINS * ntiles;
-    char *tp = (char *)temp;
-    int *ghist = (int *)tp;
-    tp += align256((size_t)(hist + 1) * 4);
-    int *goff = (int *)tp;
-    tp += align256((size_t)(hist + 1) * 4);
-    void *scan_tmp = tp;
-    const size_t scan_tmp_bytes = temp_bytes - (size_t)(tp - (char *)temp);
-
     const int npass = (end_bit - begin_bit + RS_BITS - 1) / RS_BITS;
-    // an even number of ping-pongs would leave the result in *_in: copy instead of constraining callers
+    if (npass > 8) return cudaErrorInvalidValue;
+    const int ntiles = (int)cdiv(n, OS_TILE);
+    unsigned *ghist = (unsigned *)temp;
+    unsigned *counters = ghist + 8 * RS_BINS;
+    unsigned *status = (unsigned *)((char *)temp + align256((size_t)(8 * RS_BINS + 8) * 4));
+    cudaMemsetAsync(temp, 0, align256((size_t)(8 * RS_BINS + 8) * 4) + (size_t)npass * ntiles * RS_BINS * 4, st);
+    sph_note(2 + npass);
+    int hb = (int)cdiv(n, RS_THREADS * 16);
+    hb = hb < 1 ? 1 : (hb > 148 * 8 ? 148 * 8 : hb);
+    os_hist_kernel<<<hb, RS_THREADS, 0, st>>>(keys_in, n, n_dev, begin_bit, npass, ghist);
+    os_prefix_kernel<<<1, RS_THREADS, 0, st>>>(ghist, npass);
     uint64_t *ka = keys_in, *kb = keys_out;
     int *va = vals_in, *vb = vals_out;
     for (int p = 0; p < npass; ++p) {
-        const int shift = begin_bit + p * RS_BITS;
-        sph_note(2);
-        rs_hist_kernel<<<ntiles, RS_THREADS, 0, st>>>(ka, n, n_dev, shift, ghist, ntiles);
-        cudaError_t e = sph_exclusive_scan(ghist, goff, hist, scan_tmp, scan_tmp_bytes, st);
-        if (e != cudaSuccess) return e;
-        rs_scatter_kernel<<<ntiles, RS_THREADS, 0, st>>>(ka, va, kb, vb, n, n_dev, shift, goff, ntiles);
+        os_pass_kernel<<<ntiles, RS_THREADS, 0, st>>>(ka, va, kb, vb, n, n_dev, begin_bit + p * RS_BITS, ghist + p * RS_BINS,
+                                                      status + (size_t)p * ntiles * RS_BINS, counters + p);
         uint64_t *tk = ka; ka = kb; kb = tk;
         int *tv = va; va = vb; vb = tv;
     }

@@ -59,6 +59,17 @@ cudaError_t dalloc(T **p, size_t n) {
     return cudaMalloc((void **)p, n * sizeof(T) + 256);
 }
 
+// grow-only device scratch of the handle (getters, density_at): no cudaMalloc / cudaFree per call
+int ensure_scratch(sph_handle *h, size_t bytes) {
+    if (bytes <= h->scratch_bytes) return SPH_OK;
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->scratch) cudaFree(h->scratch);
+    h->scratch = nullptr; h->scratch_bytes = 0;
+    SPH_CUDA(h, cudaMalloc(&h->scratch, bytes + 256));
+    h->scratch_bytes = bytes;
+    return SPH_OK;
+}
+
 __global__ void sticky_kernel(unsigned long long *scal) { scal[SC_STICKY] |= scal[SC_ERR]; }
 
 __global__ void export_tree_kernel(SphTree t, const unsigned long long *__restrict__ scal, double m, int64_t cap,
@@ -90,6 +101,22 @@ __global__ void export_tree_centres_kernel(SphTree t, const unsigned long long *
     }
 }
 
+// FP64 FMA microbenchmark: 8 independent dependency chains per thread, 16 resident warps per scheduler-quad; the
+// result is stored so that the loop cannot be removed
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, double *__restrict__ out) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0 - 1e-9, c = 1e-9 * seed;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 int check_flags(sph_handle *h) {
     // copies the device scalars and turns sticky error flags into a status
     if (cudaMemcpyAsync(h->h_scal, h->scal, sizeof(unsigned long long) * SC_COUNT, cudaMemcpyDeviceToHost,
@@ -99,12 +126,18 @@ int check_flags(sph_handle *h) {
     const unsigned long long f = h->h_scal[SC_STICKY] | h->h_scal[SC_ERR];
     if (f) {
         cudaMemsetAsync(h->scal + SC_STICKY, 0, sizeof(unsigned long long), h->stream);
+        // the failed evaluation left stale results behind: nothing of it may be read or used as a search hint
+        h->have_eval = false; h->lists_valid = false; h->hint_valid = false; h->outputs_fresh = false;
         if (f & ERRF_DEPTH)
             return sph_fail(h, SPH_ERR_TREE_DEPTH,
-                            "octree: two particles share all 21 octant levels (coincident particles?); the "
-                            "reference's build_octree! does not terminate on such input");
+                            "octree: two particles share all " + std::to_string(SPH_LEVELS) + " octant levels (coincident particles?); "
+                            "the reference's build_octree! does not terminate on coincident input");
         if (f & ERRF_NODES) return sph_fail(h, SPH_ERR_TREE_NODES, "octree: node pool exhausted (set SPH_B200_NODE_FACTOR)");
-        return sph_fail(h, SPH_ERR_CUDA, "tree walk stack overflow");
+        if (f & ERRF_STACK) return sph_fail(h, SPH_ERR_CUDA, "tree walk stack overflow");
+        if (f & ERRF_NAN)
+            return sph_fail(h, SPH_ERR_NAN, "time step is NaN (non-finite state); the reference's `while t < tEnd` loop ends here "
+                                            "because minimum() propagates NaN (F/isothermal_sim.jl:158-166)");
+        return sph_fail(h, SPH_ERR_CUDA, "device error flag " + std::to_string((unsigned long long)f));
     }
     return SPH_OK;
 }
@@ -251,6 +284,38 @@ int sph_device_count(void) {
     return n;
 }
 
+int sph_measure_fp64_peak(int device, double *tflops) {
+    if (!tflops) return sph_fail(nullptr, SPH_ERR_INVALID, "sph_measure_fp64_peak: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return sph_fail(nullptr, SPH_ERR_NO_DEVICE, "sph_measure_fp64_peak: no such CUDA device");
+    }
+    const int blocks = 148 * 8, threads = 256, iters = 2048;
+    double *buf = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&buf, (size_t)blocks * threads * sizeof(double));
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    float best = 0.f;
+    for (int rep = 0; rep < 5 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(e0, 0);
+        fp64_peak_kernel<<<blocks, threads>>>(iters, 1.0 + rep, buf);
+        cudaEventRecord(e1, 0);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms > 0.f && (best == 0.f || ms < best)) best = ms;     // rep 0 warms up
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (buf) cudaFree(buf);
+    if (e != cudaSuccess || best <= 0.f) return sph_fail(nullptr, SPH_ERR_CUDA, std::string("sph_measure_fp64_peak: ") + cudaGetErrorString(e));
+    *tflops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads / ((double)best * 1e-3) / 1e12;
+    return SPH_OK;
+}
+
 const char *sph_last_error(const sph_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
 int sph_create(const sph_params *p, sph_handle **out) {
@@ -331,6 +396,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(dalloc(&h->red_partial, (size_t)592 * 12));
     for (int i = 0; i <= PH_COUNT; ++i) CK(cudaEventCreate(&h->ev[i]));
     for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&h->cev[i]));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&h->wev[i]));
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -359,12 +425,17 @@ int sph_destroy(sph_handle *h) {
                     h->tree.bfs_of_old, h->tree.level_start};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (h->scratch) cudaFree(h->scratch);
+    if (h->log_dev) cudaFree(h->log_dev);
+    if (h->h_log) cudaFreeHost(h->h_log);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->h_stat) cudaFreeHost(h->h_stat);
     for (int i = 0; i <= PH_COUNT; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 6; ++i)
         if (h->cev[i]) cudaEventDestroy(h->cev[i]);
+    for (int i = 0; i < 2; ++i)
+        if (h->wev[i]) cudaEventDestroy(h->wev[i]);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -464,8 +535,18 @@ int sph_step(sph_handle *h, int nsteps, sph_step_info *info) {
     if (nsteps == 0) return SPH_OK;
     SPH_CUDA(h, cudaSetDevice(h->p.device));
     const bool poly = h->p.eos == SPH_EOS_POLYTROPIC;
-    double *log_dev = nullptr;
-    SPH_CUDA(h, cudaMalloc((void **)&log_dev, (size_t)nsteps * 11 * sizeof(double)));
+    // step log {dt, stats row} x nsteps: device buffer + pinned mirror owned by the handle (grown on demand)
+    if ((size_t)nsteps > h->log_cap) {
+        SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->log_dev) cudaFree(h->log_dev);
+        if (h->h_log) cudaFreeHost(h->h_log);
+        h->log_dev = nullptr; h->h_log = nullptr; h->log_cap = 0;
+        const size_t cap = (size_t)nsteps < 256 ? 256 : (size_t)nsteps;
+        SPH_CUDA(h, cudaMalloc((void **)&h->log_dev, cap * 11 * sizeof(double)));
+        SPH_CUDA(h, cudaMallocHost((void **)&h->h_log, cap * 11 * sizeof(double)));
+        h->log_cap = cap;
+    }
+    double *log_dev = h->log_dev;
     int rc = SPH_OK;
     for (int s = 0; s < nsteps && rc == SPH_OK; ++s) {
         // getAcc #1, dt, statistics                                   F/isothermal_sim.jl:155-192
@@ -485,19 +566,18 @@ int sph_step(sph_handle *h, int nsteps, sph_step_info *info) {
         if (e == cudaSuccess) e = sph_launch_correct(h);
         if (e != cudaSuccess) { rc = sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e)); break; }
     }
-    if (rc == SPH_OK) rc = check_flags(h);
     if (rc == SPH_OK && info) {
-        double *tmp = (double *)malloc((size_t)nsteps * 11 * sizeof(double));
-        cudaError_t e = cudaMemcpy(tmp, log_dev, (size_t)nsteps * 11 * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpyAsync(h->h_log, log_dev, (size_t)nsteps * 11 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
         if (e != cudaSuccess) rc = sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e));
-        for (int s = 0; s < nsteps && rc == SPH_OK; ++s) {
-            info[s].dt = tmp[(size_t)s * 11];
-            for (int k = 0; k < 10; ++k) info[s].stats[k] = tmp[(size_t)s * 11 + 1 + k];
-        }
-        free(tmp);
     }
-    cudaStreamSynchronize(h->stream);
-    cudaFree(log_dev);
+    if (rc == SPH_OK) rc = check_flags(h);        // synchronises the stream
+    else cudaStreamSynchronize(h->stream);
+    if (rc == SPH_OK && info) {
+        for (int s = 0; s < nsteps; ++s) {
+            info[s].dt = h->h_log[(size_t)s * 11];
+            for (int k = 0; k < 10; ++k) info[s].stats[k] = h->h_log[(size_t)s * 11 + 1 + k];
+        }
+    }
     h->lists_valid = h->lists_valid && rc == SPH_OK;
     return rc;
 }
@@ -507,21 +587,16 @@ int sph_get_neighbors(sph_handle *h, int32_t *idx, double *r) {
     if (!h->have_eval || !h->lists_valid) return sph_fail(h, SPH_ERR_STATE, "sph_get_neighbors: no force evaluation yet");
     SPH_CUDA(h, cudaSetDevice(h->p.device));
     const size_t NK = (size_t)h->N * (size_t)h->K;
-    int *d_idx = nullptr;
-    double *d_r = nullptr;
-    if (idx) SPH_CUDA(h, cudaMalloc((void **)&d_idx, NK * 4));
-    if (r) SPH_CUDA(h, cudaMalloc((void **)&d_r, NK * 8));
-    if (h->nranks > 1) {  // rows of other ranks' targets are not held here
-        if (d_idx) cudaMemsetAsync(d_idx, 0, NK * 4, h->stream);
-        if (d_r) cudaMemsetAsync(d_r, 0, NK * 8, h->stream);
-        cudaFree(d_idx); cudaFree(d_r);
+    if (h->nranks > 1)   // rows of other ranks' targets are not held here
         return sph_fail(h, SPH_ERR_STATE, "sph_get_neighbors: only available on single-GPU handles");
-    }
+    const size_t off_r = (NK * 4 + 255) & ~(size_t)255;
+    if (int rc = ensure_scratch(h, off_r + NK * 8)) return rc;
+    int *d_idx = idx ? (int *)h->scratch : nullptr;
+    double *d_r = r ? (double *)((char *)h->scratch + off_r) : nullptr;
     cudaError_t e = sph_launch_export_neighbors(h, d_idx, d_r);
     if (e == cudaSuccess && idx) e = cudaMemcpyAsync(idx, d_idx, NK * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && r) e = cudaMemcpyAsync(r, d_r, NK * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_idx); cudaFree(d_r);
     if (e != cudaSuccess) return sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e));
     return SPH_OK;
 }
@@ -573,13 +648,12 @@ int sph_get_octree(sph_handle *h, double *nodes, int64_t cap, int64_t *n_nodes) 
     if (!nodes) return SPH_OK;
     const int64_t n = M < cap ? M : cap;
     if (n <= 0) return SPH_OK;
-    double *d = nullptr;
-    SPH_CUDA(h, cudaMalloc((void **)&d, (size_t)n * 16 * 8));
+    if (int rc = ensure_scratch(h, (size_t)n * 16 * 8)) return rc;
+    double *d = (double *)h->scratch;
     export_tree_kernel<<<148 * 4, 256, 0, h->stream>>>(h->tree, h->scal, h->p.m, n, d);
     export_tree_centres_kernel<<<148 * 4, 256, 0, h->stream>>>(h->tree, h->scal, h->keys, n, d);
     cudaError_t e = cudaMemcpyAsync(nodes, d, (size_t)n * 16 * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d);
     if (e != cudaSuccess) return sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e));
     return SPH_OK;
 }
@@ -604,6 +678,11 @@ int sph_get_timings(sph_handle *h, sph_timings *out) {
         out->force_ms = f;
     }
     out->gravity_ms = ms[PH_GRAV];
+    {
+        float w = 0.f;
+        SPH_CUDA(h, cudaEventElapsedTime(&w, h->wev[0], h->wev[1]));
+        out->walk_kernel_ms = w;
+    }
     out->finish_ms = ms[PH_FINISH];
     float tot;
     SPH_CUDA(h, cudaEventElapsedTime(&tot, h->ev[0], h->ev[PH_COUNT]));
@@ -643,15 +722,13 @@ int sph_density_at(sph_handle *h, const double *pts, int64_t M, double *rho_out)
     SPH_CUDA(h, sph_launch_domain_keys(h, h->pos));
     SPH_CUDA(h, sph_launch_permute(h, h->pos, h->vel, nullptr));
     SPH_CUDA(h, sph_launch_tree(h));
-    double *d_pts = nullptr, *d_rho = nullptr;
-    SPH_CUDA(h, cudaMalloc((void **)&d_pts, (size_t)M * 3 * 8));
-    SPH_CUDA(h, cudaMalloc((void **)&d_rho, (size_t)M * 8));
+    if (int rc = ensure_scratch(h, (size_t)M * (4 + (size_t)h->K) * 8)) return rc;
+    double *d_pts = (double *)h->scratch, *d_rho = d_pts + 3 * M, *d_d2s = d_rho + M;
     cudaError_t e = cudaMemcpyAsync(d_pts, pts, (size_t)M * 3 * 8, cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = sph_launch_knn_points(h, d_pts, M, d_rho);
+    if (e == cudaSuccess) e = sph_launch_knn_points(h, d_pts, M, d_d2s, d_rho);
     if (e == cudaSuccess) e = cudaMemcpyAsync(rho_out, d_rho, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream);
     sticky_kernel<<<1, 1, 0, h->stream>>>(h->scal);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_pts); cudaFree(d_rho);
     if (e != cudaSuccess) return sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e));
     return check_flags(h);
 }

@@ -195,9 +195,14 @@ struct sph_handle {
     double *stat_dev = nullptr;            // 32 doubles: t, dt, reduction results, stats row (integrate.cu)
     double *h_stat = nullptr;              // pinned mirror
     double *red_partial = nullptr;         // per-block partial sums of the statistics kernels
+    double *log_dev = nullptr, *h_log = nullptr;   // step log {dt, stats row} of sph_step: device + pinned mirror
+    size_t log_cap = 0;                            // steps
+    void *scratch = nullptr;                       // grow-only scratch of the getters / density_at
+    size_t scratch_bytes = 0;
     // timing
     cudaEvent_t ev[PH_COUNT + 1]{};
     cudaEvent_t cev[6]{};   // begin/end of the three collectives
+    cudaEvent_t wev[2]{};   // the walk kernel alone
     // the force kernel (+ its all-reduce) runs on a second stream, concurrently with the tree walk: both only need
     // the density/EOS results, and the latency-bound force kernel fills the issue slots the walk's tail leaves idle
     cudaStream_t stream2 = nullptr;
@@ -214,7 +219,7 @@ struct sph_handle {
 
 // scal[0..SC_RESET) is cleared at the start of every force evaluation; SC_STICKY accumulates error flags
 enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_KNN_RETRY, SC_RESET = 15, SC_STICKY = 15, SC_COUNT = 16 };
-enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4 };
+enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4, ERRF_NAN = 8 };
 
 int sph_fail(sph_handle *h, int code, const std::string &msg);
 // cumulative count of kernel launches issued by the library in this process (bench.py's gpu_launches)
@@ -246,7 +251,7 @@ cudaError_t sph_launch_tree(sph_handle *h);
 // ---- knn.cu --------------------------------------------------------------------------------------
 cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1);
 cudaError_t sph_launch_export_neighbors(sph_handle *h, int *idx_out_dev, double *r_out_dev);
-cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t M, double *rho_out_dev);
+cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t M, double *d2s_dev /* M x K scratch */, double *rho_out_dev);
 
 // ---- hydro.cu ------------------------------------------------------------------------------------
 cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1);

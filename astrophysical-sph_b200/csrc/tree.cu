@@ -9,7 +9,7 @@
 //   * a stable counting sort of that (start, depth) list by depth gives exactly the node order of
 //     build_octree!'s breadth-first loop (:217-223), so children of a node are contiguous;
 //   * cell geometry replays the reference's centre/bounds recurrence bit for bit (sph_cell_of);
-//   * masses / centres of mass are accumulated level by level from the deepest level up, children in
+//   * masses / centres of mass are accumulated bottom-up in one launch (arrival counters), children in
 //     octant order, as setCOMs! does in its reverse sweep (:183-211).
 #include <cstdlib>
 
@@ -39,6 +39,9 @@ __global__ void __launch_bounds__(TB) absmax_kernel(const double *__restrict__ p
         for (int w = 1; w < TB / 32; ++w) mx = fmax(mx, sm[w]);
         // non-negative doubles order like their bit patterns
         atomicMax(&scal[SC_LDOM], (unsigned long long)__double_as_longlong(mx));
+        // an error of an earlier evaluation that the host has not collected yet (sph_step enqueues several evaluations
+        // before it reads the flags) keeps the following evaluations from running on the broken state
+        if (blockIdx.x == 0 && scal[SC_STICKY] != 0ull) atomicOr(&scal[SC_ERR], scal[SC_STICKY]);
     }
 }
 
@@ -238,32 +241,6 @@ __global__ void __launch_bounds__(TB) com_bottomup_kernel(SphTree t, const unsig
     }
 }
 
-// internal nodes of one level: Mass = sum of child masses, rCOM = sum(M_c * rCOM_c) / Mass, children in
-// octant order (setCOMs!, F/gravOctree_Single.jl:197-208).  No FMA: the reference rounds each product.
-__global__ void __launch_bounds__(TB) com_level_kernel(int level, const int *__restrict__ level_start, SphTree t) {
-    const int k0 = level_start[level], k1 = level_start[level + 1];
-    for (int k = k0 + blockIdx.x * blockDim.x + threadIdx.x; k < k1; k += gridDim.x * blockDim.x) {
-        const int2 I = t.nodeI[k];
-        if (I.y == 0) continue;
-        double tm = 0.0, wx = 0.0, wy = 0.0, wz = 0.0;
-        for (int c = 0; c < (I.y & 0xff); ++c) {
-            const double4 A = t.nodeA[I.x + c];
-            tm = __dadd_rn(tm, A.w);
-            wx = __dadd_rn(wx, __dmul_rn(A.w, A.x));
-            wy = __dadd_rn(wy, __dmul_rn(A.w, A.y));
-            wz = __dadd_rn(wz, __dmul_rn(A.w, A.z));
-        }
-        const double cx = wx / tm, cy = wy / tm, cz = wz / tm;
-        t.nodeA[k] = make_double4(cx, cy, cz, tm);
-        // radius of the cell about its COM (upper bound): lets the walk prove clause 2 of the acceptance test
-        // (h_i^2 / mindist^2 < 0.25) from d alone, since mindist >= d - radius
-        const double4 B = t.nodeB[k];
-        const double4 C = t.nodeC[k];
-        const double rx = fmax(cx - B.x, B.w - cx), ry = fmax(cy - B.y, C.x - cy), rz = fmax(cz - B.z, C.y - cz);
-        t.nodeD[k] = make_double2(C.z, sqrt(rx * rx + ry * ry + rz * rz) * (1.0 + 1e-12));
-    }
-}
-
 }  // namespace
 
 cudaError_t sph_launch_domain_keys(sph_handle *h, const double *pos) {
@@ -286,7 +263,7 @@ cudaError_t sph_launch_tree(sph_handle *h) {
     cudaStream_t st = h->stream;
     SphTree &t = h->tree;
     const int64_t N = h->N;
-    sph_note(5 + SPH_LEVELS);
+    sph_note(6);
     node_count_kernel<<<grid_for(N), TB, 0, st>>>(h->keys, N, h->cnt, h->scal);
     cudaError_t e = sph_exclusive_scan(h->cnt, h->base, N, h->sort_tmp, h->sort_tmp_bytes, st);
     if (e != cudaSuccess) return e;
@@ -300,13 +277,7 @@ cudaError_t sph_launch_tree(sph_handle *h) {
     node_inverse_kernel<<<grid_for(t.cap), TB, 0, st>>>(t.dval_out, t.old_depth, h->scal, t.bfs_of_old, t.level_start);
     node_build_kernel<<<grid_for(t.cap), TB, 0, st>>>(h->keys, N, h->cnt, h->base, t.dval_out, t.old_start,
                                                        t.old_depth, t.bfs_of_old, h->pos4, h->p.m, h->scal, t);
-    static const bool by_level = getenv("SPH_B200_COM_LEVELS") != nullptr;
-    if (by_level) {
-        for (int lev = SPH_LEVELS - 1; lev >= 0; --lev)
-            com_level_kernel<<<grid_for(N / 4 + 1), TB, 0, st>>>(lev, t.level_start, t);
-    } else {
-        cudaMemsetAsync(t.arrive, 0, sizeof(int) * (size_t)t.cap, st);
-        com_bottomup_kernel<<<grid_for(t.cap), TB, 0, st>>>(t, h->scal);
-    }
+    cudaMemsetAsync(t.arrive, 0, sizeof(int) * (size_t)t.cap, st);
+    com_bottomup_kernel<<<grid_for(t.cap), TB, 0, st>>>(t, h->scal);
     return cudaGetLastError();
 }

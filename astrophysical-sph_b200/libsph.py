@@ -20,18 +20,19 @@ LIB_PATH = os.path.join(_HERE, "libsph_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 ISOTHERMAL, POLYTROPIC = 0, 1
+FLAG_COUNT_VISITS = 1       # sph_params.flags: count the node visits of the tree walk (timings()["walk_visits"])
 EOS_CODES = {"isothermal": ISOTHERMAL, "polytropic": POLYTROPIC}
 
 SPH_OK = 0
 SPH_ERR_INVALID, SPH_ERR_CUDA, SPH_ERR_NO_DEVICE, SPH_ERR_TREE_DEPTH = -1, -2, -3, -4
-SPH_ERR_TREE_NODES, SPH_ERR_NCCL, SPH_ERR_STATE = -5, -6, -7
+SPH_ERR_TREE_NODES, SPH_ERR_NCCL, SPH_ERR_STATE, SPH_ERR_NAN = -5, -6, -7, -8
 
 # every symbol include/sph_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = (
     "sph_create", "sph_destroy", "sph_last_error", "sph_abi_version", "sph_launch_count", "sph_device_count", "sph_set_stream",
     "sph_synchronize", "sph_upload", "sph_download", "sph_eval_acc", "sph_eval_state", "sph_step",
     "sph_get_neighbors", "sph_get_hydro", "sph_get_grav", "sph_get_acc", "sph_get_octree", "sph_get_timings",
-    "sph_get_dt", "sph_density_at", "sph_comm_unique_id", "sph_comm_init",
+    "sph_get_dt", "sph_density_at", "sph_comm_unique_id", "sph_comm_init", "sph_measure_fp64_peak",
 )
 
 
@@ -47,7 +48,8 @@ class SphStepInfo(C.Structure):
 
 class SphTimings(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("sort_ms", "tree_ms", "knn_ms", "density_ms", "force_ms", "gravity_ms",
-                                          "finish_ms", "total_ms", "walk_visits", "knn_retries", "comm_ms")]
+                                          "finish_ms", "total_ms", "walk_visits", "knn_retries", "comm_ms",
+                                          "walk_kernel_ms")]
 
 
 class SphError(RuntimeError):
@@ -95,6 +97,15 @@ def device_count() -> int:
     return int(lib().sph_device_count())
 
 
+def measure_fp64_peak(device: int = 0) -> float:
+    """Measured FP64 FMA throughput of `device` in TFLOP/s (the library's own DFMA microbenchmark)."""
+    v = C.c_double(0.0)
+    rc = lib().sph_measure_fp64_peak(int(device), C.byref(v))
+    if rc != 0:
+        raise SphError(rc, lib().sph_last_error(None).decode())
+    return v.value
+
+
 def _f64(a, order="F"):
     return np.require(a, dtype=np.float64, requirements=["F_CONTIGUOUS" if order == "F" else "C_CONTIGUOUS", "ALIGNED"])
 
@@ -107,12 +118,12 @@ class SphB200:
     """One handle = one B200.  Mirrors the data flow of run_simulation (F/isothermal_sim.jl:72-298)."""
 
     def __init__(self, N, Kh=50, eos="isothermal", m=1.0, cs=0.0, gamma=5.0 / 3, G=6.6743e-8, theta=0.576, alpha=1.0,
-                 beta=2.0, U_iso=0.0, device=0):
+                 beta=2.0, U_iso=0.0, device=0, flags=0):
         self._h = C.c_void_p()
         self.N, self.Kh = int(N), int(Kh)
         self.eos = EOS_CODES[eos] if isinstance(eos, str) else int(eos)
         p = SphParams(self.N, self.Kh, self.eos, float(m), float(cs), float(gamma), float(G), float(theta),
-                      float(alpha), float(beta), float(U_iso), int(device), 0)
+                      float(alpha), float(beta), float(U_iso), int(device), int(flags))
         self.params = p
         rc = lib().sph_create(C.byref(p), C.byref(self._h))
         if rc != 0:

@@ -5,13 +5,15 @@
   python bench.py --impl reference [...]                        the CPU restatement of the reference's Julia
                                                                 path (oracle/, OpenMP over all host cores) --
                                                                 the Julia reference itself cannot run here.
+  python bench.py --config c0|c1|c2|c3|c4 [--scaling weak]      the other BASELINE.json configs (c2 = default)
   N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): BASELINE.json configs[2] -- Boss-Bodenheimer rotating isothermal cloud, N = 1e6
+Default workload (config.workload): BASELINE.json configs[2] -- Boss-Bodenheimer rotating isothermal cloud, N = 1e6
 particles, Kh = 50, theta = 0.576 (F/iniconds.jl:457-525 distributions, numpy default_rng(42), T = 10 K).
 One step = one iteration of `while t < tEnd` (F/isothermal_sim.jl:152-213): two full force evaluations
 (sort, octree, exact kNN, density, force, tree walk) + dt + statistics + predictor + corrector.
-Prints ONE JSON line (rank 0).
+Prints ONE JSON line (rank 0).  With several ranks a 20 000-particle run is first compared with the oracle
+("parity" in the line; a violation makes the exit code non-zero).
 """
 import argparse
 import json
@@ -24,9 +26,27 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# BASELINE.json configs -> (EOS, ic_type, N, extra iniconds arguments)
+CONFIGS = {
+    "c0": ("polytropic", "gaussian_sphere", 5_000, dict(R=5.38552341e16)),
+    "c1": ("polytropic", "sample_plummer_sphere", 100_000, {}),
+    "c2": ("isothermal", "boss_bodenheimer", 1_000_000, dict(T=10)),
+    "c3": ("isothermal", "turbulent_molecular_cloud", 4_000_000, dict(T=10)),
+    "c4": ("isothermal", "bonnor_ebert_sphere", 16_000_000, dict(T=10)),
+}
+
 # algorithmic (compulsory) FP64 bytes per particle per force evaluation, SURVEY.md section 8(d), Kh = 50
 ALG_BYTES = {"knn": 232.0, "density": 232.0, "force": 296.0, "gravity": 123.0}
-ALG_BYTES_STEP = 2.0 * sum(ALG_BYTES.values()) + 240.0   # + integrator streams
+# algorithmic FP64 flops, SURVEY.md section 8(d): 45 per node visit of the walk; density 16 Kh, force 60 x 2 x (Kh - 2)
+FLOPS_PER_VISIT = 45.0
+FLOPS_SPH = {"density": 16.0 * 50, "force": 60.0 * 2 * 48}
+
+
+def alg_bytes(eos):
+    b = dict(ALG_BYTES)
+    if eos == "polytropic":
+        b["force"] = 312.0
+    return b
 
 
 def peaks():
@@ -37,11 +57,26 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_workload(n):
+def make_workload(cfg, n):
     import astrophysical_sph_b200.iniconds as ic
 
-    d = ic.make_ic("isothermal", "boss_bodenheimer", N=n, T=10)
-    return d["pos"], d["vel"], d["constants"]
+    eos, ic_type, _, kw = CONFIGS[cfg]
+    d = ic.make_ic(eos, ic_type, N=n, **kw)
+    return eos, d["pos"], d["vel"], d["K"], d["constants"]
+
+
+def workload_name(cfg, n):
+    eos, ic_type, n0, _ = CONFIGS[cfg]
+    return f"{ic_type} {eos} N={n} Kh=50 theta=0.576 (BASELINE.json configs[{cfg[1]}]{'' if n == n0 else ', N overridden'})"
+
+
+def sph_args(eos, c):
+    a = dict(m=c["m"], G=c["G"], theta=c["theta"], alpha=c["alpha"], beta=c["beta"])
+    if eos == "isothermal":
+        a.update(cs=c["cs"], U_iso=c["U"])
+    else:
+        a.update(gamma=c["gamma"])
+    return a
 
 
 class ClockSampler:
@@ -87,37 +122,43 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_reference_steps(pos, vel, c, nsteps, nthreads):
+def cpu_reference_steps(eos, pos, vel, K, c, nsteps, nthreads):
     """nsteps loop iterations on the oracle (all phases, same code path the parity tests check against)."""
     from oracle import oracle as O
 
+    kw = dict(eos=O.ISOTHERMAL, cs=c["cs"], U_iso=c["U"]) if eos == "isothermal" else dict(eos=O.POLYTROPIC, Kent=K, gamma=c["gamma"])
     t0 = time.perf_counter()
-    O.step(pos, vel, c["m"], c["Kh"], c["G"], c["theta"], 0.0, nsteps, eos=O.ISOTHERMAL, cs=c["cs"], alpha=c["alpha"],
-           beta=c["beta"], U_iso=c["U"], nthreads=nthreads)
+    O.step(pos, vel, c["m"], c["Kh"], c["G"], c["theta"], 0.0, nsteps, alpha=c["alpha"], beta=c["beta"], nthreads=nthreads, **kw)
     return time.perf_counter() - t0
 
 
+def total_n(args, world):
+    n0 = CONFIGS[args.config][2]
+    if args.scaling == "weak":
+        per = args.n if args.n else max(n0 // 8, 1000)
+        return per * world
+    return args.n if args.n else n0
+
+
 def run_reference(args, rank, world):
+    """The reference arm: the oracle (C++ restatement of the Julia path) on all host cores, SAME workload and N as the
+    GPU arm.  Each step is a full step (about 14 s at N = 1e6 on 16 cores); only the warm-up is capped at one step."""
     if rank != 0:
         return
     nt = host_threads()
-    total = args.steps + args.warmup
-    # bounded sample: the same IC family at a particle count that keeps the whole run within a few minutes
-    n = args.n if total <= 8 else max(100_000, int(args.n * 8 / total) // 1000 * 1000)
-    n = min(n, args.n)
-    pos, vel, c = make_workload(n)
+    n = total_n(args, world)
+    eos, pos, vel, K, c = make_workload(args.config, n)
     if args.warmup:
-        cpu_reference_steps(pos, vel, c, min(args.warmup, 1), nt)
-    dt = cpu_reference_steps(pos, vel, c, args.steps, nt)
+        cpu_reference_steps(eos, pos, vel, K, c, 1, nt)
+    dt = cpu_reference_steps(eos, pos, vel, K, c, args.steps, nt)
     val = n * args.steps / dt
     line = {
         "impl": "reference", "metric": "particle_steps_per_s", "value": val, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"boss_bodenheimer isothermal N={n} Kh=50 theta=0.576 (CPU sample of the N={args.n} workload)",
-                   "N": n, "Kh": 50},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, n), "N": n, "Kh": 50, "theta": 0.576, "force_evals_per_step": 2},
         "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": nt, "kind": "port",
-                         "sample": f"{args.steps} full steps at N={n} (warmup capped at 1 step), OpenMP x{nt}; "
+                         "sample": f"{args.steps} full steps at N={n} (warm-up capped at 1 step), OpenMP x{nt}; "
                                    "Julia reference not runnable (no Julia toolchain)"},
         "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -126,8 +167,11 @@ def run_reference(args, rank, world):
 
 
 def run_b200(args, rank, world, local_rank):
+    import ctypes as C
+
     import torch
 
+    from astrophysical_sph_b200 import libsph
     from astrophysical_sph_b200.libsph import SphB200, launch_count
 
     dist = None
@@ -139,11 +183,24 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank
     torch.cuda.set_device(dev)
-    n = args.n
-    pos, vel, c = make_workload(n)
+
+    # ---- multi-GPU parity against the oracle before anything is timed
+    parity = None
+    if world > 1:
+        from tools.mgpu_check import run_check
+
+        parity, ok = run_check(dist, rank, world, dev, 20000)
+        if not ok:
+            if rank == 0:
+                print(json.dumps({"metric": "particle_steps_per_s", "n_gpus": world, "parity": parity,
+                                  "error": "multi-GPU parity against the oracle FAILED"}), flush=True)
+            dist.destroy_process_group()
+            sys.exit(1)
+
+    n = total_n(args, world)
+    eos, pos, vel, K, c = make_workload(args.config, n)
     stream = torch.cuda.Stream(device=dev)
-    s = SphB200(n, c["Kh"], "isothermal", m=c["m"], cs=c["cs"], G=c["G"], theta=c["theta"], alpha=c["alpha"],
-                beta=c["beta"], U_iso=c["U"], device=dev)
+    s = SphB200(n, c["Kh"], eos, device=dev, **sph_args(eos, c))
     s.set_stream(stream.cuda_stream)
     if world > 1:
         box = [SphB200.comm_unique_id() if rank == 0 else None]
@@ -164,7 +221,7 @@ def run_b200(args, rank, world, local_rank):
         return float(t.item())
 
     # ---- device-resident stepping ("value")
-    s.upload(pos, vel, None, 0.0)
+    s.upload(pos, vel, K, 0.0)
     if args.warmup:
         s.step(args.warmup, want_info=False)
     barrier()
@@ -182,22 +239,26 @@ def run_b200(args, rank, world, local_rank):
     tim = s.timings()      # phases of the last force evaluation inside the timed region
     value = n * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the public API with host buffers ("e2e")
+    # ---- end to end through the public API with host buffers ("e2e"): every rank passes the full pinned arrays,
+    # the library moves 1/world of them over PCIe per rank and exchanges the slices over NVLink; rank 0 reads the result
+    npoly = 1 if eos == "polytropic" else 0
     hp = torch.empty((3, n), dtype=torch.float64).pin_memory()
     hv = torch.empty((3, n), dtype=torch.float64).pin_memory()
-    hp_np, hv_np = hp.numpy().T, hv.numpy().T            # (N, 3) Fortran-ordered views of pinned memory
-    hp_np[...] = pos; hv_np[...] = vel
-    import ctypes as C
-
-    from astrophysical_sph_b200.libsph import lib as _lib
-
-    L = _lib()
+    hk = torch.empty((n,), dtype=torch.float64).pin_memory() if npoly else None
+    hp.numpy().T[...] = pos
+    hv.numpy().T[...] = vel             # (N, 3) Fortran-ordered views of pinned memory
+    if npoly:
+        hk.numpy()[...] = K
+    L = libsph.lib()
     tt = C.c_double(0.0)
+    kp = C.c_void_p(hk.data_ptr()) if npoly else None
+    down = rank == 0
 
     def e2e_step():
-        s._chk(L.sph_upload(s._h, C.c_void_p(hp.data_ptr()), C.c_void_p(hv.data_ptr()), None, C.c_double(tt.value)))
+        s._chk(L.sph_upload(s._h, C.c_void_p(hp.data_ptr()), C.c_void_p(hv.data_ptr()), kp, C.c_double(tt.value)))
         s._chk(L.sph_step(s._h, 1, None))
-        s._chk(L.sph_download(s._h, C.c_void_p(hp.data_ptr()), C.c_void_p(hv.data_ptr()), None, C.byref(tt)))
+        s._chk(L.sph_download(s._h, C.c_void_p(hp.data_ptr()) if down else None, C.c_void_p(hv.data_ptr()) if down else None,
+                              kp if down else None, C.byref(tt)))
 
     e2e_step()
     barrier()
@@ -208,6 +269,19 @@ def run_b200(args, rank, world, local_rank):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_val = n * args.steps / e2e_s
 
+    # ---- node visits per particle of the walk (algorithmic flops of the dominant kernel): one counted evaluation on
+    # a second handle (rank 0, one GPU's share is the same fraction of it)
+    visits = None
+    fp64_peak = None
+    if rank == 0:
+        fp64_peak = libsph.measure_fp64_peak(dev)
+    if world == 1:
+        s2 = SphB200(n, c["Kh"], eos, device=dev, flags=libsph.FLAG_COUNT_VISITS, **sph_args(eos, c))
+        s2.upload(pos, vel, K, 0.0)
+        s2.eval_state()
+        visits = s2.timings()["walk_visits"] / n
+        s2.close()
+
     if rank != 0:
         s.close()
         if dist is not None:
@@ -215,66 +289,88 @@ def run_b200(args, rank, world, local_rank):
         return
 
     peak, peak_src = peaks()
+    AB = alg_bytes(eos)
+    nt_targets = n / world
     phases = {}
     for k in ("knn", "density", "force", "gravity"):
         t_ms = tim[k + "_ms"]
-        nt_targets = n / world
-        gbs = ALG_BYTES[k] * nt_targets / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
-        phases[k] = {"ms": round(t_ms, 4), "alg_bytes_per_particle": ALG_BYTES[k], "achieved_gbs": round(gbs, 2),
-                     "frac": round(gbs / peak, 5)}
-    for k in ("sort", "tree", "finish", "total"):
+        gbs = AB[k] * nt_targets / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+        phases[k] = {"ms": round(t_ms, 4), "alg_bytes_per_particle": AB[k], "achieved_gbs": round(gbs, 2),
+                     "frac_hbm": round(gbs / peak, 5)}
+    for k in ("sort", "tree", "finish", "total", "walk_kernel"):
         phases[k] = {"ms": round(tim[k + "_ms"], 4)}
     dom = max(("knn", "density", "force", "gravity"), key=lambda k: phases[k]["ms"])
+    kernel_of = {"knn": "knn_quad_kernel", "gravity": "walk_pairs_kernel", "force": "force_kernel", "density": "density_kernel"}
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get(dom)
     sph_ms = phases["density"]["ms"] + phases["force"]["ms"]
-    sph_gbs = (ALG_BYTES["density"] + ALG_BYTES["force"]) * (n / world) / (sph_ms * 1e-3) / 1e9
+    sph_gbs = (AB["density"] + AB["force"]) * nt_targets / (sph_ms * 1e-3) / 1e9
+    sph_tf = (FLOPS_SPH["density"] + FLOPS_SPH["force"]) * nt_targets / (sph_ms * 1e-3) / 1e12
+
+    # roofline of the dominant kernel.  The tree walk is bound by the FP64 pipe / instruction issue, not by HBM
+    # (SURVEY.md 8d): `bound` names what binds, the HBM fraction on compulsory bytes is reported beside it.
+    if dom == "gravity":
+        k_ms = tim["walk_kernel_ms"] if tim["walk_kernel_ms"] > 0 else tim["gravity_ms"]
+        v = visits if visits is not None else 904.0
+        tf = FLOPS_PER_VISIT * v * nt_targets / (k_ms * 1e-3) / 1e12
+        gbs = AB["gravity"] * nt_targets / (k_ms * 1e-3) / 1e9
+        roof = {"bound": "fp64", "kernel": kernel_of[dom], "achieved": round(tf, 3), "peak": round(fp64_peak, 2), "unit": "TFLOP/s",
+                "frac": round(tf / fp64_peak, 4), "traffic": traffic, "kernel_ms": round(k_ms, 4),
+                "alg_flops_per_particle": FLOPS_PER_VISIT * v, "node_visits_per_particle": round(v, 2),
+                "peak_source": "measured: sph_measure_fp64_peak (own DFMA microbenchmark on this GPU, this run)",
+                "hbm": {"achieved": round(gbs, 2), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 5),
+                        "alg_bytes_per_particle": AB["gravity"], "peak_source": peak_src},
+                "note": "algorithmic flops and bytes per SURVEY.md 8(d): 45 flop per node visit x visits counted by the "
+                        "kernel itself (second handle, SPH_FLAG_COUNT_VISITS), 123 B per particle"}
+    else:
+        roof = {"bound": "hbm", "kernel": kernel_of[dom], "achieved": phases[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": phases[dom]["frac_hbm"], "traffic": traffic, "peak_source": peak_src}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         nt = host_threads()
-        dtc = cpu_reference_steps(pos, vel, c, 1, nt)
-        cpu = {"value": n / dtc, "unit": "particle-steps/s", "cores": nt, "kind": "port",
-               "sample": f"1 full step of the same N={n} workload on the oracle (C++ restatement of the Julia path, "
+        ncpu = min(n, 1_000_000)
+        if ncpu == n:
+            ce, cp, cv, cK, cc = eos, pos, vel, K, c
+        else:
+            ce, cp, cv, cK, cc = make_workload(args.config, ncpu)
+        dtc = cpu_reference_steps(ce, cp, cv, cK, cc, 1, nt)
+        cpu = {"value": ncpu / dtc, "unit": "particle-steps/s", "cores": nt, "kind": "port",
+               "sample": f"1 full step of the N={ncpu} workload on the oracle (C++ restatement of the Julia path, "
                          f"OpenMP x{nt}), {dtc:.1f} s"}
 
+    h2d = (48 + 8 * npoly) * n // world
     line = {
         "metric": "particle_steps_per_s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"boss_bodenheimer isothermal N={n} Kh=50 theta=0.576 T=10K (BASELINE.json configs[2])",
-                   "N": n, "Kh": 50, "theta": 0.576, "force_evals_per_step": 2,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, n), "N": n, "Kh": 50, "theta": 0.576, "force_evals_per_step": 2,
                    "parallelism": "single GPU" if world == 1 else f"targets split by Morton-key range over {world} ranks, "
-                                                                   "replicated state, NCCL all-gather/all-reduce",
-                   "l2": "working set (neighbour lists 200 MB + tree 150 MB + state) exceeds the 126 MB L2; no explicit flush"},
+                                                                   "replicated state, NCCL all-gathers",
+                   "l2": "working set (neighbour lists 200 B + tree 190 B + state per particle) exceeds the 126 MB L2 "
+                         "at N >= 1e6; no explicit flush"},
         "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * n + 8,
+        "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (48 + 8 * npoly) * n + 8,
                 "ms_per_step": 1e3 * e2e_s / args.steps,
-                "api": "sph_upload + sph_step(1) + sph_download on pinned host buffers, every step"},
+                "api": "sph_upload + sph_step(1) + sph_download on pinned host buffers, every step"
+                       + ("" if world == 1 else f"; per rank 1/{world} of the upload over PCIe, slices exchanged over NVLink; rank 0 downloads")},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": {"knn": "knn_quad_kernel", "gravity": "walk_pairs_kernel", "force": "force_kernel",
-                                                "density": "density_kernel"}[dom],
-                     "achieved": phases[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": phases[dom]["frac"],
-                     "traffic": traffic, "peak_source": peak_src,
-                     "note": "algorithmic bytes per SURVEY.md 8(d); these kernels are FP64-pipe / latency bound, not HBM bound "
-                             "(DESIGN.md section 4); fp64 = SURVEY 8(d) algorithmic flops (45 per node visit, 904 visits per "
-                             "particle at this N) against the nominal 37 TFLOP/s FP64 peak",
-                     "fp64": {"gravity_tflops": round(45.0 * 904.0 * (n / world) / (phases["gravity"]["ms"] * 1e-3) / 1e12, 3),
-                              "peak_nominal_tflops": 37.0,
-                              "frac": round(45.0 * 904.0 * (n / world) / (phases["gravity"]["ms"] * 1e-3) / 1e12 / 37.0, 4)}},
-        "sph_sums": {"ms": round(sph_ms, 4), "achieved_gbs": round(sph_gbs, 2), "frac": round(sph_gbs / peak, 5),
-                     "alg_bytes_per_particle": ALG_BYTES["density"] + ALG_BYTES["force"]},
-        "step_alg_bytes": {"per_particle_step": ALG_BYTES_STEP,
-                           "achieved_gbs": round(ALG_BYTES_STEP * value / 1e9, 2),
-                           "frac": round(ALG_BYTES_STEP * value / 1e9 / peak, 5)},
+        "roofline": roof,
+        "fp64_peak_tflops": round(fp64_peak, 2),
+        "sph_sums": {"ms": round(sph_ms, 4), "achieved_gbs": round(sph_gbs, 2), "frac_hbm": round(sph_gbs / peak, 5),
+                     "alg_bytes_per_particle": AB["density"] + AB["force"],
+                     "achieved_tflops": round(sph_tf, 3), "frac_fp64": round(sph_tf / fp64_peak, 4),
+                     "alg_flops_per_particle": FLOPS_SPH["density"] + FLOPS_SPH["force"]},
         "phases_last_eval": phases,
         "knn_retries": tim.get("knn_retries"),
         "comm_ms_last_eval": tim.get("comm_ms"),
         "cpu_baseline": cpu,
     }
+    if parity is not None:
+        line["parity"] = parity
     print(json.dumps(line), flush=True)
     s.close()
     if dist is not None:
@@ -287,7 +383,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: N fixed (the metric's definition); weak: N = n x world (n per GPU, default config N / 8)")
+    ap.add_argument("--n", type=int, default=0, help="override the particle count (per GPU with --scaling weak)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -300,7 +399,8 @@ def main():
         # replicas are not what the metric asks for: re-launch under torchrun so that ranks share one job
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"), __file__,
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--n", str(args.n)]
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--config", args.config,
+               "--scaling", args.scaling, "--n", str(args.n)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
         sys.exit(subprocess.call(cmd))
     run_b200(args, rank, world, local_rank)
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPH_B200_ABI_VERSION 1
+#define SPH_B200_ABI_VERSION 2
 
 enum sph_eos {
     SPH_EOS_ISOTHERMAL = 0, /* P = cs^2 rho            F/isothermal_hydroKDTree.jl:181-193 */
@@ -39,9 +39,12 @@ enum sph_status {
     SPH_ERR_NO_DEVICE = -3,   /* no sm_100 device visible: the library never falls back to the CPU             */
     SPH_ERR_TREE_DEPTH = -4,  /* two particles share all 21 octant levels (coincident or closer than l/2^21);
                                  the reference loops forever here (F/gravOctree_Single.jl:217-223)              */
-    SPH_ERR_TREE_NODES = -5,  /* node pool exhausted even after regrowth                                       */
+    SPH_ERR_TREE_NODES = -5,  /* node pool (3 N + 1024 nodes; SPH_B200_NODE_FACTOR enlarges it) exhausted         */
     SPH_ERR_NCCL = -6,        /* NCCL call failed                                                              */
-    SPH_ERR_STATE = -7        /* call sequence error (e.g. sph_step before sph_upload)                         */
+    SPH_ERR_STATE = -7,       /* call sequence error (e.g. sph_step before sph_upload)                         */
+    SPH_ERR_NAN = -8          /* the adaptive time step came out NaN (non-finite state).  The reference's
+                                 minimum() propagates NaN, t becomes NaN and `while t < tEnd` ends
+                                 (F/isothermal_sim.jl:152,158-166); here the step is refused instead            */
 };
 
 /* Run-time physics parameters = the `constants` row of a snapshot (F/SnapshotRW.jl:86-97) that
@@ -59,8 +62,11 @@ typedef struct sph_params {
     double beta;    /* artificial viscosity beta                                             */
     double U_iso;   /* constant thermal energy "U" of an isothermal snapshot (stats only)    */
     int32_t device; /* CUDA device ordinal of this handle (one process per GPU)              */
-    int32_t flags;  /* reserved, 0                                                           */
+    int32_t flags;  /* SPH_FLAG_* bits, 0 by default                                         */
 } sph_params;
+
+/* sph_params.flags */
+#define SPH_FLAG_COUNT_VISITS 1 /* count the node visits of the tree walk (sph_timings.walk_visits); slows the walk */
 
 /* One row of the reference's stats matrix (F/isothermal_sim.jl:189-192) plus the step's dt. */
 typedef struct sph_step_info {
@@ -82,7 +88,9 @@ typedef struct sph_timings {
     double total_ms;
     double walk_visits;  /* sum over targets of node visits in the last walk (0 unless SPH_B200_COUNT_VISITS) */
     double knn_retries;  /* targets whose hinted search radius held < Kh particles and was repeated           */
-    double comm_ms;      /* of the above: time inside the three NCCL collectives (0 on a single GPU)         */
+    double comm_ms;      /* of the above: time inside the NCCL collectives (0 on a single GPU)               */
+    double walk_kernel_ms; /* the tree-walk kernel alone (gravity_ms also holds the record packing, the partial-sum
+                              reduction and, on several GPUs, the result all-gather)                            */
 } sph_timings;
 
 typedef struct sph_handle sph_handle;
@@ -99,6 +107,9 @@ int sph_abi_version(void);
 int64_t sph_launch_count(void);
 /* Number of CUDA devices visible (0 = none; never an error).  */
 int sph_device_count(void);
+/* Measured FP64 FMA throughput of `device` in TFLOP/s (own DFMA microbenchmark, a few milliseconds): the denominator of
+ * the FP64 roofline bench.py reports for the tree walk and the SPH sums (not a reference interface). */
+int sph_measure_fp64_peak(int device, double *tflops);
 /* Run the handle's work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = own stream). */
 int sph_set_stream(sph_handle *h, void *cuda_stream);
 int sph_synchronize(sph_handle *h);

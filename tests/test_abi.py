@@ -33,7 +33,7 @@ def test_header_symbols_all_exported(libsph):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/sph_b200.h but not exported"
     assert sorted(libsph.ABI_SYMBOLS) == names
-    assert lib.sph_abi_version() == 1
+    assert lib.sph_abi_version() == 2
 
 
 def test_library_is_sm100a_only(libsph):

@@ -29,10 +29,11 @@ def child(N, tag):
     s = SphB200(N, c["Kh"], "isothermal", m=c["m"], cs=c["cs"], G=c["G"], theta=c["theta"], alpha=c["alpha"], beta=c["beta"],
                 U_iso=c["U"])
     s.upload(pos, vel, None, 0.0)
-    ms = []
+    ms, km = [], []
     for _ in range(4):
         s.eval_acc(pos, vel, None)
         ms.append(s.timings()["gravity_ms"])
+        km.append(s.timings()["walk_kernel_ms"])
     tm = s.timings()
     g, phi = s.grav()
     s.close()
@@ -45,7 +46,7 @@ def child(N, tag):
         dev = "  dev vs first cfg: g %.2e phi %.2e" % (eg.max(), ep.max())
     else:
         np.savez(ref, g=g, phi=phi)
-    print("%-44s grav_ms %s  visits/particle %.2f%s" % (tag, " ".join("%.3f" % x for x in ms), tm["walk_visits"] / N, dev),
+    print("%-44s grav_ms %s  kernel_ms %s  visits/particle %.2f%s" % (tag, " ".join("%.3f" % x for x in ms), " ".join("%.3f" % x for x in km), tm["walk_visits"] / N, dev),
           flush=True)
 
 
