@@ -75,7 +75,7 @@ __device__ __forceinline__ void knn_compact(double *bd2, int *bid, const int *__
 // SELF = true : queries are the sorted particles themselves (targets t0..t1), output = neighbour lists
 // SELF = false: queries are arbitrary points (density_plot), output = the K sorted squared distances
 template <int CAP, bool SELF>
-__global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_kernel(int64_t N, int K, int64_t t0, int64_t t1,
+__global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_kernel(int64_t N, int64_t NL, int K, int64_t t0, int64_t t1,
                                                               const double4 *__restrict__ pos4,
                                                               const double *__restrict__ qpts, int64_t qstride,
                                                               const int *__restrict__ perm, SphTree t,
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_kernel(int64_t N, int K
                                                               const int *__restrict__ list,
                                                               unsigned long long *__restrict__ scal,
                                                               int *__restrict__ nbr, double *__restrict__ d2k,
-                                                              double *__restrict__ d2_out) {
+                                                              int *__restrict__ kid, double *__restrict__ d2_out) {
     __shared__ double s_d2[KNN_WARPS][CAP];
     __shared__ int s_id[KNN_WARPS][CAP];
     __shared__ int s_stack[KNN_WARPS][KNN_STACK];
@@ -207,8 +207,11 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_kernel(int64_t N, int K
             warp_bitonic<CAP>(bd2, bid, perm, lane);
         }
         if (SELF) {
-            for (int j = lane; j < K; j += 32) nbr[s + (int64_t)j * N] = bid[j];
-            if (lane == 0) d2k[s] = bd2[K - 1];
+            for (int j = lane; j < K; j += 32) nbr[s + (int64_t)j * NL] = bid[j];
+            // kid: caller's particle id of the K-th entry.  A particle at exactly the K-th distance belongs to this
+            // list iff its id is <= kid (the tie order of the sort above): hydro.cu decides list membership from
+            // (d2k, kid) alone, without reading other targets' lists
+            if (lane == 0) { d2k[s] = bd2[K - 1]; kid[s] = perm[bid[K - 1]]; }
         } else {
             for (int j = lane; j < K; j += 32) d2_out[s + (int64_t)j * qstride] = bd2[j];
         }
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_kernel(int64_t N, int K
 // sph_get_neighbors: one warp per row orders the (possibly unordered) list by (distance, particle id) and writes
 // the reference's layout: N x K column-major, 1-based caller ids, ascending distance (F/isothermal_hydroKDTree.jl:131-142)
 template <int CAP>
-__global__ void __launch_bounds__(KNN_WARPS * 32) export_sorted_kernel(int64_t N, int K, const double4 *__restrict__ pos4,
+__global__ void __launch_bounds__(KNN_WARPS * 32) export_sorted_kernel(int64_t N, int64_t NL, int K, const double4 *__restrict__ pos4,
                                                                         const int *__restrict__ perm,
                                                                         const int *__restrict__ nbr,
                                                                         int *__restrict__ idx_out, double *__restrict__ r_out) {
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) export_sorted_kernel(int64_t N
         const double4 q = pos4[s];
         for (int j = lane; j < CAP; j += 32) {
             if (j < K) {
-                const int nj = nbr[s + (int64_t)j * N];
+                const int nj = nbr[s + (int64_t)j * NL];
                 const double4 p = pos4[nj];
                 bd2[j] = sph_d2_exact(q.x - p.x, q.y - p.y, q.z - p.z);
                 bid[j] = nj;
@@ -316,13 +319,14 @@ __device__ __forceinline__ void kq_cex(unsigned long long &k, int &v, unsigned l
 }
 
 template <int BLOCKS>
-__global__ void __launch_bounds__(KQ_WARPS * 32, BLOCKS) knn_quad_kernel(int64_t N, int K, int64_t t0, int64_t t1,
+__global__ void __launch_bounds__(KQ_WARPS * 32, BLOCKS) knn_quad_kernel(int64_t N, int64_t NL, int K, int64_t t0, int64_t t1,
                                                                     const double4 *__restrict__ pos4,
                                                                     const int *__restrict__ perm, SphTree t,
                                                                     const double *__restrict__ hint_h, double hint_fac2,
                                                                     int sel_steps, int bucket, unsigned long long *__restrict__ scal,
                                                                     int *__restrict__ retry_list,
-                                                                    int *__restrict__ nbr, double *__restrict__ d2k) {
+                                                                    int *__restrict__ nbr, double *__restrict__ d2k,
+                                                                    int *__restrict__ kid) {
     __shared__ KqWarp s_w[KQ_WARPS];
     if (scal[SC_ERR] != 0ull) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -536,10 +540,10 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, BLOCKS) knn_quad_kernel(int64_t
                     for (int r = 0; r < KQ_CAP / 32; ++r) {
                         const bool sel = key[r] <= kth;
                         const unsigned sb = __ballot_sync(0xffffffffu, sel);
-                        if (sel) nbr[s + (int64_t)(base + __popc(sb & lt)) * N] = vid[r];
+                        if (sel) nbr[s + (int64_t)(base + __popc(sb & lt)) * NL] = vid[r];
                         base += __popc(sb);
                     }
-                    if (lane == 0) d2k[s] = __longlong_as_double((long long)kth);
+                    if (lane == 0) { d2k[s] = __longlong_as_double((long long)kth); kid[s] = INT_MAX; }   // no tie at the K-th distance
                 }
             }
             if (found) {
@@ -574,10 +578,11 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, BLOCKS) knn_quad_kernel(int64_t
                 const bool t1e = lane < 31 && nx1 == k1 && k1 != ~0ull;
                 tie = __any_sync(0xffffffffu, t0e || t1e);
                 if (!tie) {
-                    if (lane < K) nbr[s + (int64_t)lane * N] = v0;
-                    if (lane + 32 < K) nbr[s + (int64_t)(lane + 32) * N] = v1;
+                    if (lane < K) nbr[s + (int64_t)lane * NL] = v0;
+                    if (lane + 32 < K) nbr[s + (int64_t)(lane + 32) * NL] = v1;
                     if (lane == K - 1) d2k[s] = __longlong_as_double((long long)k0);
                     if (lane + 32 == K - 1) d2k[s] = __longlong_as_double((long long)k1);
+                    if (lane == 0) kid[s] = INT_MAX;
                 }
             } else {
                 // rank sort: count the entries that precede each of the lane's three
@@ -606,8 +611,8 @@ __global__ void __launch_bounds__(KQ_WARPS * 32, BLOCKS) knn_quad_kernel(int64_t
 #pragma unroll
                     for (int r = 0; r < KQ_CAP / 32; ++r) {
                         if (e_id[r] >= 0 && e_rank[r] < K) {
-                            nbr[s + (int64_t)e_rank[r] * N] = e_id[r];
-                            if (e_rank[r] == K - 1) d2k[s] = __longlong_as_double((long long)e_k[r]);
+                            nbr[s + (int64_t)e_rank[r] * NL] = e_id[r];
+                            if (e_rank[r] == K - 1) { d2k[s] = __longlong_as_double((long long)e_k[r]); kid[s] = INT_MAX; }
                         }
                     }
                 }
@@ -649,33 +654,33 @@ cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1) {
         // SPH_B200_KNN_SORT=1: always order the hits with the sort network instead of selecting the K-th distance
         static const int sel_steps = getenv("SPH_B200_KNN_SORT") ? 0 : KQ_SEL_STEPS;
         const int bucket = 32;             // cells up to this many particles are scanned as ranges (<= KQ_BUCKET)
-        knn_quad_kernel<KQ_BLOCKS><<<(int)blocks, KQ_WARPS * 32, 0, h->stream>>>(h->N, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2,
-                                                                                sel_steps, bucket, h->scal, h->cnt, h->nbr, h->d2k);
+        knn_quad_kernel<KQ_BLOCKS><<<(int)blocks, KQ_WARPS * 32, 0, h->stream>>>(h->N, h->NL, h->K, t0, t1, h->pos4, h->perm, h->tree, hint, fac2,
+                                                                                sel_steps, bucket, h->scal, h->cnt, h->nbr, h->d2k, h->kid);
         // queued targets keep their own hinted ball (only the shared box was too wide); a failing hint falls back to
         // the guaranteed radius inside the kernel
         knn_kernel<128, true><<<148 * 5, KNN_WARPS * 32, 0, h->stream>>>(
-            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, 1.1 * 1.1, h->cnt, h->scal, h->nbr, h->d2k, nullptr);
+            h->N, h->NL, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, 1.1 * 1.1, h->cnt, h->scal, h->nbr, h->d2k, h->kid, nullptr);
         return cudaGetLastError();
     }
     sph_note(1);
     const int blocks = knn_blocks(t1 - t0);
     if (h->K <= 96)
         knn_kernel<128, true><<<blocks, KNN_WARPS * 32, 0, h->stream>>>(
-            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, fac2, nullptr, h->scal, h->nbr, h->d2k, nullptr);
+            h->N, h->NL, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, fac2, nullptr, h->scal, h->nbr, h->d2k, h->kid, nullptr);
     else
         knn_kernel<256, true><<<blocks, KNN_WARPS * 32, 0, h->stream>>>(
-            h->N, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, fac2, nullptr, h->scal, h->nbr, h->d2k, nullptr);
+            h->N, h->NL, h->K, t0, t1, h->pos4, nullptr, 0, h->perm, h->tree, hint, fac2, nullptr, h->scal, h->nbr, h->d2k, h->kid, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t sph_launch_export_neighbors(sph_handle *h, int *idx_out_dev, double *r_out_dev) {
     sph_note(1);
     if (h->K <= 64)
-        export_sorted_kernel<64><<<148 * 8, KNN_WARPS * 32, 0, h->stream>>>(h->N, h->K, h->pos4, h->perm, h->nbr, idx_out_dev, r_out_dev);
+        export_sorted_kernel<64><<<148 * 8, KNN_WARPS * 32, 0, h->stream>>>(h->N, h->NL, h->K, h->pos4, h->perm, h->nbr, idx_out_dev, r_out_dev);
     else if (h->K <= 128)
-        export_sorted_kernel<128><<<148 * 8, KNN_WARPS * 32, 0, h->stream>>>(h->N, h->K, h->pos4, h->perm, h->nbr, idx_out_dev, r_out_dev);
+        export_sorted_kernel<128><<<148 * 8, KNN_WARPS * 32, 0, h->stream>>>(h->N, h->NL, h->K, h->pos4, h->perm, h->nbr, idx_out_dev, r_out_dev);
     else
-        export_sorted_kernel<256><<<148 * 8, KNN_WARPS * 32, 0, h->stream>>>(h->N, h->K, h->pos4, h->perm, h->nbr, idx_out_dev, r_out_dev);
+        export_sorted_kernel<256><<<148 * 8, KNN_WARPS * 32, 0, h->stream>>>(h->N, h->NL, h->K, h->pos4, h->perm, h->nbr, idx_out_dev, r_out_dev);
     return cudaGetLastError();
 }
 
@@ -686,10 +691,10 @@ cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t 
     const int blocks = knn_blocks(M);
     if (h->K <= 96)
         knn_kernel<128, false><<<blocks, KNN_WARPS * 32, 0, h->stream>>>(
-            h->N, h->K, 0, M, h->pos4, pts_dev, M, h->perm, h->tree, nullptr, 1.0, nullptr, h->scal, nullptr, nullptr, d2s);
+            h->N, h->NL, h->K, 0, M, h->pos4, pts_dev, M, h->perm, h->tree, nullptr, 1.0, nullptr, h->scal, nullptr, nullptr, nullptr, d2s);
     else
         knn_kernel<256, false><<<blocks, KNN_WARPS * 32, 0, h->stream>>>(
-            h->N, h->K, 0, M, h->pos4, pts_dev, M, h->perm, h->tree, nullptr, 1.0, nullptr, h->scal, nullptr, nullptr, d2s);
+            h->N, h->NL, h->K, 0, M, h->pos4, pts_dev, M, h->perm, h->tree, nullptr, 1.0, nullptr, h->scal, nullptr, nullptr, nullptr, d2s);
     point_density_kernel<<<(int)((M + 127) / 128), 128, 0, h->stream>>>(M, h->K, d2s, h->p.m,
                                                                          h->p.eos == SPH_EOS_POLYTROPIC, rho_out_dev);
     return cudaGetLastError();

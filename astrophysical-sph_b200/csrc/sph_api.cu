@@ -154,11 +154,17 @@ int nccl_fail(sph_handle *h, ncclResult_t r, const char *what) {
 #define TRACE(msg) do { if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[sph_b200 trace] %s (%s)\n", msg, cudaGetErrorString(cudaGetLastError())); } } while (0)
 
 // One getAcc on device arrays in the caller's particle order.
+//
+// Several ranks: every rank holds the full state and repeats the (cheap) sort + tree; rank r owns the targets
+// [r * chunk, (r + 1) * chunk) of the key order for search / density / force and tiles dealt round-robin for the walk.
+// Nothing is reduced across ranks - the force is a gather (hydro.cu) - so every exchange is an all-gather of results:
+//   d2k + kid (12 B per particle) after the search, rho + the cross-rank reverse pairs after the density,
+//   the six force outputs (48 B) on the second stream beside the walk, g + PHI (32 B) after the walk.
 int eval_internal(sph_handle *h, const double *pos, const double *vel, const double *kent, double *acc_out) {
     cudaStream_t st = h->stream;
     const int64_t N = h->N;
     const bool multi = h->nranks > 1;
-    const int64_t chunk = h->NS / h->nranks;
+    const int64_t chunk = h->chunk;
     int64_t t0 = (int64_t)h->rank * chunk, t1 = t0 + chunk;
     if (t0 > N) t0 = N;
     if (t1 > N) t1 = N;
@@ -178,42 +184,36 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     SPH_CUDA(h, sph_launch_knn(h, t0, t1));
     TRACE("sph_launch_knn done");
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_KNN + 1], st));
+    // ---- density + EOS phase
+    if (multi) {   // list membership tests and the smoothing lengths need the K-th distance of every particle
+        SPH_CUDA(h, cudaEventRecord(h->cev[0], st));
+        SPH_NCCL(h, nc.GroupStart());
+        SPH_NCCL(h, nc.AllGather(h->d2k + h->rank * chunk, h->d2k, (size_t)chunk, ncclDouble, comm, st));
+        SPH_NCCL(h, nc.AllGather(h->kid + h->rank * chunk, h->kid, (size_t)chunk, ncclInt32, comm, st));
+        SPH_NCCL(h, nc.GroupEnd());
+        SPH_CUDA(h, cudaEventRecord(h->cev[1], st));
+    }
+    SPH_CUDA(h, sph_launch_smoothing(h));
+    SPH_CUDA(h, sph_launch_density(h, t0, t1));
+    TRACE("sph_launch_density done");
+    if (multi) {   // rho of all particles; reverse pairs that point at other ranks' targets
+        SPH_CUDA(h, sph_launch_outbox_header(h));
+        SPH_CUDA(h, cudaEventRecord(h->cev[2], st));
+        SPH_NCCL(h, nc.GroupStart());
+        SPH_NCCL(h, nc.AllGather(h->rho_s + h->rank * chunk, h->rho_s, (size_t)chunk, ncclDouble, comm, st));
+        SPH_NCCL(h, nc.AllGather(h->outbox, h->inbox, (size_t)(h->obcap + 1) * 2, ncclInt32, comm, st));
+        SPH_NCCL(h, nc.GroupEnd());
+        SPH_CUDA(h, cudaEventRecord(h->cev[3], st));
+        SPH_CUDA(h, sph_launch_extras_merge(h, t0, t1));
+    }
+    SPH_CUDA(h, sph_launch_eos(h));
+    SPH_CUDA(h, sph_launch_extras_sort(h, t0, t1));
+    TRACE("sph_launch_eos done");
+    SPH_CUDA(h, cudaEventRecord(h->ev[PH_DENSITY + 1], st));
+    // ---- force (second stream when overlapping) || walk (main stream)
     const bool ov = h->overlap && (!multi || h->nccl2 != nullptr);
     cudaStream_t fs = ov ? h->stream2 : st;
-    // SPH_B200_DENSITY_OVERLAP=1 (single GPU, opt-in): the walk only needs h (not rho), which is a function of the K-th
-    // distance alone, so pos4.w is set right after the search and density + EOS + force all run on stream2 beside the
-    // walk.  Measured 9.97 vs 10.07 ms per evaluation, but the density kernel is then time-sliced with the walk and its
-    // phase time no longer says anything about the kernel, so the default keeps it in front of the fork.  With several
-    // ranks h of the other ranks' targets arrives with the {h, rho} all-gather anyway.
-    static const bool dens_overlap = getenv("SPH_B200_DENSITY_OVERLAP") != nullptr;
-    const bool dov = ov && !multi && dens_overlap;
-    h->density_overlapped = dov;
-    if (dov) {
-        SPH_CUDA(h, sph_launch_smoothing(h));
-        SPH_CUDA(h, cudaEventRecord(h->ev_fork, st));
-        SPH_CUDA(h, cudaStreamWaitEvent(fs, h->ev_fork, 0));
-        SPH_CUDA(h, cudaEventRecord(h->dev[0], fs));
-        h->stream = fs;
-        cudaError_t de = sph_launch_density(h, t0, t1);
-        if (de == cudaSuccess) de = sph_launch_eos(h, false);
-        h->stream = st;
-        SPH_CUDA(h, de);
-        SPH_CUDA(h, cudaEventRecord(h->dev[1], fs));
-        TRACE("density + eos enqueued on stream2");
-    } else {
-        SPH_CUDA(h, sph_launch_density(h, t0, t1));
-        TRACE("sph_launch_density done");
-        if (multi) {  // every rank needs h and rho of all particles (neighbours of its targets, leaf softening)
-            SPH_CUDA(h, cudaEventRecord(h->cev[0], st));
-            SPH_NCCL(h, nc.AllGather(h->hr + h->rank * chunk, h->hr, (size_t)chunk * 2, ncclDouble, comm, st));
-            SPH_CUDA(h, cudaEventRecord(h->cev[1], st));
-        }
-        SPH_CUDA(h, sph_launch_eos(h, true));
-        TRACE("sph_launch_eos done");
-    }
-    SPH_CUDA(h, cudaEventRecord(h->ev[PH_DENSITY + 1], st));
-    // ---- force (stream2 when overlapping) || walk (main stream): the walk depends on h only
-    if (ov && !dov) {
+    if (ov) {
         SPH_CUDA(h, cudaEventRecord(h->ev_fork, st));
         SPH_CUDA(h, cudaStreamWaitEvent(fs, h->ev_fork, 0));
     }
@@ -224,12 +224,14 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     SPH_CUDA(h, fe);
     TRACE("sph_launch_force done");
     if (multi) {
-        // reactions a_j += ct*gradW land on particles of other ranks: sum the partial accelerations
-        // (also carries sum_vdw and mumax of the owned targets: the other ranks hold zeros there)
-        SPH_CUDA(h, cudaEventRecord(h->cev[2], fs));
-        SPH_NCCL(h, nc.AllReduce(h->s_red, h->s_red, (size_t)h->NS * 6, ncclDouble, ncclSum,
-                                 ov ? (ncclComm_t)h->nccl2 : comm, fs));
-        SPH_CUDA(h, cudaEventRecord(h->cev[3], fs));
+        ncclComm_t fc = ov ? (ncclComm_t)h->nccl2 : comm;
+        SPH_CUDA(h, cudaEventRecord(h->cev[4], fs));
+        SPH_NCCL(h, nc.GroupStart());
+        for (int c = 0; c < 6; ++c)
+            SPH_NCCL(h, nc.AllGather(h->s_red + (size_t)c * h->NS + h->rank * chunk, h->s_red + (size_t)c * h->NS, (size_t)chunk,
+                                     ncclDouble, fc, fs));
+        SPH_NCCL(h, nc.GroupEnd());
+        SPH_CUDA(h, cudaEventRecord(h->cev[5], fs));
     }
     SPH_CUDA(h, cudaEventRecord(h->fev[1], fs));
     if (ov) SPH_CUDA(h, cudaEventRecord(h->ev_join, fs));
@@ -237,10 +239,10 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     SPH_CUDA(h, sph_launch_walk(h));
     TRACE("sph_launch_walk done");
     if (multi) {
-        SPH_CUDA(h, cudaEventRecord(h->cev[4], st));
+        SPH_CUDA(h, cudaEventRecord(h->cev[6], st));
         SPH_NCCL(h, nc.AllGather(h->walk_buf + (size_t)h->rank * 4 * h->walk_chunk, h->walk_buf, (size_t)4 * h->walk_chunk,
                                  ncclDouble, comm, st));
-        SPH_CUDA(h, cudaEventRecord(h->cev[5], st));
+        SPH_CUDA(h, cudaEventRecord(h->cev[7], st));
     }
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_GRAV + 1], st));
     if (ov) SPH_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
@@ -255,6 +257,33 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     h->hint_valid = true;
     h->last_acc = acc_out;
     return SPH_OK;
+}
+
+// sizes that depend on the rank count: targets per rank (a multiple of 128, so list tiles never straddle ranks and
+// stay 16-byte aligned), stride of the component arrays, walk tiles per rank
+void set_partition(sph_handle *h, int nranks, int rank) {
+    h->nranks = nranks;
+    h->rank = rank;
+    const int64_t per = (h->N + nranks - 1) / nranks;
+    h->chunk = (per + 127) / 128 * 128;
+    h->NS = h->chunk * nranks;
+    h->s_ahyd = h->s_red; h->s_dkdt = h->s_red + 3 * h->NS; h->s_sumvdw = h->s_red + 4 * h->NS; h->s_mumax = h->s_red + 5 * h->NS;
+    // tiles of 128 walk targets are dealt round-robin in groups of SPH_WALK_DEAL: ceil(groups / nranks) groups per rank
+    const int64_t tiles = (h->N + 127) / 128;
+    const int64_t groups = (tiles + SPH_WALK_DEAL - 1) / SPH_WALK_DEAL;
+    h->walk_chunk = (groups + nranks - 1) / nranks * SPH_WALK_DEAL * 128;
+}
+
+// sph_upload on several ranks: columns arrive as [rank][column][per] slices in `stage`
+__global__ void upload_unpack_kernel(int64_t N, int64_t per, int ncol, const double *__restrict__ stage, double *__restrict__ pos,
+                                     double *__restrict__ vel, double *__restrict__ kent) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / per, o = i - r * per;
+        const double *src = stage + (size_t)r * ncol * per + o;
+        pos[i] = src[0]; pos[i + N] = src[per]; pos[i + 2 * N] = src[2 * per];
+        vel[i] = src[3 * per]; vel[i + N] = src[4 * per]; vel[i + 2 * N] = src[5 * per];
+        if (ncol == 7) kent[i] = src[6 * per];
+    }
 }
 
 int d2h(sph_handle *h, double *dst, const double *src, size_t n) {
@@ -339,8 +368,8 @@ int sph_create(const sph_params *p, sph_handle **out) {
     h->N = p->N;
     h->K = p->Kh;
     h->no_hint = getenv("SPH_B200_NO_HINT") != nullptr;
-    const int64_t Q = 1680;  // divisible by every rank count 1..8, 10, 12, 14, 15, 16
-    h->NS = (h->N + Q - 1) / Q * Q;
+    h->NL = (h->N + 127) / 128 * 128;
+    h->NS_alloc = h->NL + 128 * SPH_MAX_RANKS;    // >= nranks * roundup(ceil(N / nranks), 128) for every rank count
 #define CK(call)                                                                                  \
     do {                                                                                          \
         cudaError_t e__ = (call);                                                                 \
@@ -353,7 +382,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(cudaSetDevice(p->device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
-    const size_t N = (size_t)h->N, NS = (size_t)h->NS, K = (size_t)h->K;
+    const size_t N = (size_t)h->N, NS = (size_t)h->NS_alloc, NL = (size_t)h->NL, K = (size_t)h->K;
     CK(dalloc(&h->pos, 3 * N)); CK(dalloc(&h->vel, 3 * N)); CK(dalloc(&h->kent, N)); CK(dalloc(&h->acc, 3 * N));
     CK(dalloc(&h->pos_half, 3 * N)); CK(dalloc(&h->vel_half, 3 * N));
     CK(dalloc(&h->in_pos, 3 * N)); CK(dalloc(&h->in_vel, 3 * N)); CK(dalloc(&h->in_kent, N)); CK(dalloc(&h->in_acc, 3 * N));
@@ -361,17 +390,27 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(dalloc(&h->o_mumax, N)); CK(dalloc(&h->o_cs, N)); CK(dalloc(&h->o_dkdt, N)); CK(dalloc(&h->o_ahyd, 3 * N));
     CK(dalloc(&h->o_g, 3 * N));
     CK(dalloc(&h->keys, N)); CK(dalloc(&h->keys_alt, N)); CK(dalloc(&h->perm, N)); CK(dalloc(&h->perm_alt, N));
-    CK(dalloc(&h->pos4, NS)); CK(dalloc(&h->vel4, NS)); CK(dalloc(&h->hr, NS)); CK(dalloc(&h->prr, NS));
-    CK(dalloc(&h->cs_s, NS)); CK(dalloc(&h->d2k, NS)); CK(dalloc(&h->nbr, N * K));
+    CK(dalloc(&h->pos4, NS)); CK(dalloc(&h->vel4, NS)); CK(dalloc(&h->hr, NS)); CK(dalloc(&h->pc, NS));
+    CK(dalloc(&h->rho_s, NS)); CK(dalloc(&h->d2k, NS)); CK(dalloc(&h->kid, NS)); CK(dalloc(&h->nbr, NL * K));
+    CK(dalloc(&h->ecnt, NL)); CK(dalloc(&h->ext, NL * (size_t)SPH_ECAP));
+    h->ovcap = (int64_t)(N / 4 > 65536 ? N / 4 : 65536);
+    CK(dalloc(&h->ovf, (size_t)h->ovcap));
+    if (const char *e = getenv("SPH_B200_ECAP")) {   // test knob: a small table exercises the overflow list
+        const int v = atoi(e);
+        h->ecap = v < 0 ? 0 : (v > SPH_ECAP ? SPH_ECAP : v);
+    }
     CK(dalloc(&h->s_red, 6 * NS));
-    h->s_ahyd = h->s_red; h->s_dkdt = h->s_red + 3 * NS; h->s_sumvdw = h->s_red + 4 * NS; h->s_mumax = h->s_red + 5 * NS;
-    h->walk_chunk = (int64_t)(((N + 127) / 128 + SPH_WALK_DEAL - 1) / SPH_WALK_DEAL) * SPH_WALK_DEAL * 128;   // nranks = 1 until sph_comm_init
-    CK(dalloc(&h->walk_buf, 4 * ((size_t)h->walk_chunk + 128 * SPH_WALK_DEAL * SPH_MAX_RANKS)));
-    CK(dalloc(&h->walk_part, 8 * 4 * (size_t)h->walk_chunk));
-    CK(dalloc(&h->cnt, N + 1)); CK(dalloc(&h->base, N + 2));
+    set_partition(h, 1, 0);
+    {   // walk buffers sized for one rank (the largest share)
+        const size_t wc = (size_t)h->walk_chunk;
+        CK(dalloc(&h->walk_buf, 4 * (wc + 128 * SPH_WALK_DEAL * SPH_MAX_RANKS)));
+        CK(dalloc(&h->walk_part, 8 * 4 * wc));
+        CK(cudaMemset(h->walk_buf, 0, 4 * (wc + 128 * SPH_WALK_DEAL * SPH_MAX_RANKS) * 8));
+    }
     CK(cudaMemset(h->hr, 0, NS * sizeof(double2)));
     CK(cudaMemset(h->s_red, 0, 6 * NS * 8));
-    CK(cudaMemset(h->walk_buf, 0, 4 * ((size_t)h->walk_chunk + 128 * SPH_WALK_DEAL * SPH_MAX_RANKS) * 8));
+    CK(cudaMemset(h->d2k, 0, NS * 8)); CK(cudaMemset(h->kid, 0, NS * 4)); CK(cudaMemset(h->rho_s, 0, NS * 8));
+    CK(dalloc(&h->cnt, N + 1)); CK(dalloc(&h->base, N + 2));
     {
         SphTree &t = h->tree;
         double factor = 3.0;
@@ -395,13 +434,12 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(cudaMallocHost((void **)&h->h_stat, 32 * sizeof(double)));
     CK(dalloc(&h->red_partial, (size_t)592 * 12));
     for (int i = 0; i <= PH_COUNT; ++i) CK(cudaEventCreate(&h->ev[i]));
-    for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&h->cev[i]));
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&h->cev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&h->wev[i]));
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->fev[0])); CK(cudaEventCreate(&h->fev[1]));
-    CK(cudaEventCreate(&h->dev[0])); CK(cudaEventCreate(&h->dev[1]));
     h->overlap = getenv("SPH_B200_NO_OVERLAP") == nullptr;
     CK(cudaDeviceSynchronize());
 #undef CK
@@ -417,8 +455,8 @@ int sph_destroy(sph_handle *h) {
     if (h->nccl && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t)h->nccl);
     void *ptrs[] = {h->pos, h->vel, h->kent, h->acc, h->pos_half, h->vel_half, h->in_pos, h->in_vel, h->in_kent,
                     h->in_acc, h->o_rho, h->o_h, h->o_phi, h->o_sumvdw, h->o_mumax, h->o_cs, h->o_dkdt, h->o_ahyd,
-                    h->o_g, h->keys, h->keys_alt, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->prr,
-                    h->cs_s, h->d2k, h->nbr, h->s_red, h->walk_buf, h->walk_part, h->cnt,
+                    h->o_g, h->keys, h->keys_alt, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->pc,
+                    h->rho_s, h->d2k, h->kid, h->nbr, h->ecnt, h->ext, h->ovf, h->outbox, h->inbox, h->s_red, h->walk_buf, h->walk_part, h->cnt,
                     h->base, h->scal, h->stat_dev, h->red_partial, h->tree.nodeI, h->tree.nodeA, h->tree.nodeB,
                     h->tree.nodeC, h->tree.nodeD, h->tree.nodeW, h->tree.nodeBC, h->tree.parent, h->tree.arrive, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
                     h->tree.old_depth, h->tree.dkey_in, h->tree.dkey_out, h->tree.dval_in, h->tree.dval_out,
@@ -432,7 +470,7 @@ int sph_destroy(sph_handle *h) {
     if (h->h_stat) cudaFreeHost(h->h_stat);
     for (int i = 0; i <= PH_COUNT; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    for (int i = 0; i < 6; ++i)
+    for (int i = 0; i < 8; ++i)
         if (h->cev[i]) cudaEventDestroy(h->cev[i]);
     for (int i = 0; i < 2; ++i)
         if (h->wev[i]) cudaEventDestroy(h->wev[i]);
@@ -441,8 +479,6 @@ int sph_destroy(sph_handle *h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int i = 0; i < 2; ++i)
         if (h->fev[i]) cudaEventDestroy(h->fev[i]);
-    for (int i = 0; i < 2; ++i)
-        if (h->dev[i]) cudaEventDestroy(h->dev[i]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SPH_OK;
@@ -475,9 +511,27 @@ int sph_upload(sph_handle *h, const double *pos, const double *vel, const double
     if (h->p.eos == SPH_EOS_POLYTROPIC && !K) return sph_fail(h, SPH_ERR_INVALID, "sph_upload: polytropic EOS needs K");
     SPH_CUDA(h, cudaSetDevice(h->p.device));
     const size_t N = (size_t)h->N;
-    SPH_CUDA(h, cudaMemcpyAsync(h->pos, pos, 3 * N * 8, cudaMemcpyHostToDevice, h->stream));
-    SPH_CUDA(h, cudaMemcpyAsync(h->vel, vel, 3 * N * 8, cudaMemcpyHostToDevice, h->stream));
-    if (K) SPH_CUDA(h, cudaMemcpyAsync(h->kent, K, N * 8, cudaMemcpyHostToDevice, h->stream));
+    if (h->nranks > 1) {
+        // every rank is given the same arrays: rank r moves rows [r * per, (r + 1) * per) of each column over PCIe and the
+        // ranks exchange their slices over NVLink (one all-gather), instead of nranks full copies through the host link
+        NcclApi &nc = nccl_api();
+        const int ncol = K ? 7 : 6;
+        const size_t per = (N + h->nranks - 1) / h->nranks;
+        const size_t r0 = (size_t)h->rank * per < N ? (size_t)h->rank * per : N;
+        const size_t cnt = r0 + per <= N ? per : N - r0;
+        double *stage = h->walk_part;             // free between evaluations; holds 32 doubles per particle
+        double *mine = stage + (size_t)h->rank * ncol * per;
+        const double *cols[7] = {pos, pos + N, pos + 2 * N, vel, vel + N, vel + 2 * N, K};
+        for (int c = 0; c < ncol && cnt > 0; ++c)
+            SPH_CUDA(h, cudaMemcpyAsync(mine + (size_t)c * per, cols[c] + r0, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+        SPH_NCCL(h, nc.AllGather(mine, stage, (size_t)ncol * per, ncclDouble, (ncclComm_t)h->nccl, h->stream));
+        sph_note(1);
+        upload_unpack_kernel<<<148 * 8, 256, 0, h->stream>>>((int64_t)N, (int64_t)per, ncol, stage, h->pos, h->vel, h->kent);
+    } else {
+        SPH_CUDA(h, cudaMemcpyAsync(h->pos, pos, 3 * N * 8, cudaMemcpyHostToDevice, h->stream));
+        SPH_CUDA(h, cudaMemcpyAsync(h->vel, vel, 3 * N * 8, cudaMemcpyHostToDevice, h->stream));
+        if (K) SPH_CUDA(h, cudaMemcpyAsync(h->kent, K, N * 8, cudaMemcpyHostToDevice, h->stream));
+    }
     SPH_CUDA(h, sph_launch_set_time(h, t));
     SPH_CUDA(h, cudaStreamSynchronize(h->stream));
     h->t = t;
@@ -667,11 +721,6 @@ int sph_get_timings(sph_handle *h, sph_timings *out) {
     for (int i = 0; i < PH_COUNT; ++i) SPH_CUDA(h, cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
     out->sort_ms = ms[PH_SORT]; out->tree_ms = ms[PH_TREE]; out->knn_ms = ms[PH_KNN];
     out->density_ms = ms[PH_DENSITY];
-    if (h->density_overlapped) {   // density + EOS ran on stream2 (beside the walk): measured there
-        float f = 0.f;
-        SPH_CUDA(h, cudaEventElapsedTime(&f, h->dev[0], h->dev[1]));
-        out->density_ms = f;
-    }
     {   // the force phase is measured on the stream it ran on (it overlaps the walk)
         float f = 0.f;
         SPH_CUDA(h, cudaEventElapsedTime(&f, h->fev[0], h->fev[1]));
@@ -692,7 +741,7 @@ int sph_get_timings(sph_handle *h, sph_timings *out) {
     out->knn_retries = (double)h->h_scal[SC_KNN_RETRY];
     out->comm_ms = 0.0;
     if (h->nranks > 1)
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 4; ++i) {
             float c = 0.f;
             SPH_CUDA(h, cudaEventElapsedTime(&c, h->cev[2 * i], h->cev[2 * i + 1]));
             out->comm_ms += c;
@@ -747,28 +796,49 @@ int sph_comm_unique_id(void *id128) {
 
 int sph_comm_init(sph_handle *h, int nranks, int rank, const void *id128) {
     if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return sph_fail(h, SPH_ERR_INVALID, "sph_comm_init: bad argument");
-    if (h->NS % nranks != 0) return sph_fail(h, SPH_ERR_INVALID, "sph_comm_init: unsupported rank count (use 1-8, 10, 12, 14, 15 or 16)");
-    if (nranks == 1) { h->nranks = 1; h->rank = 0; return SPH_OK; }
+    if (nranks > SPH_MAX_RANKS) return sph_fail(h, SPH_ERR_INVALID, "sph_comm_init: at most 16 ranks");
+    if (h->nccl) return sph_fail(h, SPH_ERR_STATE, "sph_comm_init: the handle already belongs to a communicator");
+    if (nranks == 1) { set_partition(h, 1, 0); return SPH_OK; }
     NcclApi &nc = nccl_api();
     if (!nc.ok) return sph_fail(h, SPH_ERR_NCCL, nc.why);
     SPH_CUDA(h, cudaSetDevice(h->p.device));
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ncclComm_t comm;
     SPH_NCCL(h, nc.CommInitRank(&comm, nranks, id, rank));
     h->nccl = comm;
-    h->nranks = nranks;
-    h->rank = rank;
-    // second communicator for the stream that overlaps the force all-reduce with the walk; without ncclCommSplit the
-    // two phases simply stay on one stream
-    if (h->overlap && nc.CommSplit) {
-        ncclComm_t c2 = nullptr;
-        if (nc.CommSplit(comm, 0, rank, &c2, nullptr) == ncclSuccess) h->nccl2 = c2;
+    set_partition(h, nranks, rank);
+    h->have_eval = false; h->lists_valid = false; h->hint_valid = false;
+    // pairs {target of another rank, reverse partner}: each rank contributes up to 2 * chunk of them per evaluation
+    h->obcap = 2 * h->chunk;
+    if (const char *e = getenv("SPH_B200_HALO_CAP")) h->obcap = atoll(e) > 1024 ? atoll(e) : 1024;
+    SPH_CUDA(h, dalloc(&h->outbox, (size_t)h->obcap + 1));
+    SPH_CUDA(h, dalloc(&h->inbox, (size_t)nranks * ((size_t)h->obcap + 1)));
+    // second communicator for the stream that overlaps the force + its all-gather with the walk.  Every rank must take
+    // the same decision (a rank that kept both phases on one stream would issue its collectives on the other
+    // communicator and the job would hang): the ranks agree on min(ok) before the second communicator is used.
+    ncclComm_t c2 = nullptr;
+    int ok = h->overlap ? 1 : 0;
+    std::string split_err;
+    if (ok && !nc.CommSplit) { ok = 0; split_err = "ncclCommSplit not available"; }
+    if (ok) {
+        const ncclResult_t r = nc.CommSplit(comm, 0, rank, &c2, nullptr);
+        if (r != ncclSuccess) { ok = 0; c2 = nullptr; split_err = nc.GetErrorString(r); }
     }
-    {   // tiles of 128 walk targets are dealt round-robin: ceil(tiles / nranks) tiles per rank
-        const int64_t tiles = (h->N + 127) / 128;
-        const int64_t groups = (tiles + SPH_WALK_DEAL - 1) / SPH_WALK_DEAL;
-        h->walk_chunk = (groups + nranks - 1) / nranks * SPH_WALK_DEAL * 128;
+    int *flag = reinterpret_cast<int *>(h->scal + SC_COUNT - 1);      // SC_STICKY slot is free here: no evaluation is in flight
+    int hflag = ok;
+    SPH_CUDA(h, cudaMemcpyAsync(flag, &hflag, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    SPH_NCCL(h, nc.AllReduce(flag, flag, 1, ncclInt32, ncclMin, comm, h->stream));
+    SPH_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    SPH_CUDA(h, cudaMemsetAsync(h->scal + SC_STICKY, 0, sizeof(unsigned long long), h->stream));
+    if (hflag) {
+        h->nccl2 = c2;
+    } else {
+        if (c2) nc.CommDestroy(c2);
+        h->nccl2 = nullptr;       // force and walk share the main stream and communicator on every rank
+        if (!split_err.empty()) h->err = "note: no overlap communicator (" + split_err + "); force and walk run on one stream";
     }
     return SPH_OK;
 }

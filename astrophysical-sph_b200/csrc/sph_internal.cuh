@@ -8,7 +8,8 @@
 //   tree    BFS-ordered linear octree: nodeI int2 {first child | particle, nchild | leafmask << 8 (0 = leaf)},
 //           nodeA double4 {com, mass}, nodeB double4 {lo.xyz, hi.x}, nodeC double4 {hi.y, hi.z, (2L)^2, L}, nodeD double2 {(2L)^2, max |corner - com|},
 //           nstart/ncount i32 particle range of the node in the sorted arrays
-//   lists   nbr[N x K] i32 column-major, sorted-space rows and entries (0-based), d2k[N]
+//   lists   nbr[K x NL] i32 column-major (NL = N rounded up to 128), sorted-space rows and entries (0-based), d2k[N],
+//           kid[N] (tie id of the K-th entry); extras ext[SPH_ECAP x NL] + ecnt[N]: reverse partners outside the own list
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,6 +20,8 @@
 #define SPH_LEVELS 21           // octant levels held by one 63-bit key
 #define SPH_MAX_RANKS 16
 #define SPH_WALK_REC 2           // double4 per walk record of the octree (two nodes per 128-byte line)
+#define SPH_ECAP 64              // reverse partners per particle held in the extras table (more: overflow list)
+#define SPH_TILE_DEFAULT 0       // density / force: 1 = shared-memory tile kernels (TMA-staged), 0 = direct gathers
 #define SPH_WALK_DEAL 16         // walk tiles (128 targets) are dealt to the ranks in groups of 16 consecutive tiles:
                                  // round-robin balances the load, consecutive tiles keep the tree nodes hot in L2
 
@@ -145,7 +148,9 @@ struct SphTree {
 struct sph_handle {
     sph_params p{};
     int64_t N = 0;
-    int64_t NS = 0;  // stride of the sorted-space component arrays: N rounded up so every rank count divides it
+    int64_t NS = 0;  // stride of the sorted-space component arrays = nranks * chunk (chunk: targets per rank, a multiple of 128)
+    int64_t NS_alloc = 0;  // allocation of those arrays: covers every rank count up to SPH_MAX_RANKS
+    int64_t NL = 0;  // row stride of the neighbour lists and the extras table: N rounded up to 128
     int K = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -173,13 +178,19 @@ struct sph_handle {
     size_t sort_tmp_bytes = 0;
     // sorted working set
     double4 *pos4 = nullptr, *vel4 = nullptr;
-    double2 *hr = nullptr;
-    double *prr = nullptr;      // P/rho^2 (sorted)
-    double *cs_s = nullptr;     // sound speed (sorted)
-    double *d2k = nullptr;
-    int *nbr = nullptr;         // N x K
-    // one buffer [6][NS]: a_hyd x,y,z (direct + scattered), dK/dt sum, sum_vdw, mumax -> a single all-reduce in multi-GPU
-    // runs (only the owner of a target writes the last two, the other ranks contribute zeros)
+    double2 *hr = nullptr;      // {h, rho}
+    double4 *pc = nullptr;      // {rho, P/rho^2, d2k, c}: the record the force pass gathers per neighbour
+    double *rho_s = nullptr;    // density of the owned targets (all-gathered in multi-GPU runs)
+    double *d2k = nullptr;      // K-th squared distance
+    int *kid = nullptr;         // caller's id of the K-th list entry when the K-th distance is tied, else INT_MAX
+    int *nbr = nullptr;         // K x NL
+    // reverse partners outside the own list (hydro.cu): table, overflow list, pairs for / from other ranks
+    int *ecnt = nullptr, *ext = nullptr;
+    int2 *ovf = nullptr, *outbox = nullptr, *inbox = nullptr;
+    int ecap = SPH_ECAP;
+    int64_t ovcap = 0, obcap = 0;
+    // one buffer [6][NS]: a_hyd x,y,z, dK/dt sum, sum_vdw, mumax; every rank writes its own targets and the six
+    // component arrays are all-gathered in multi-GPU runs
     double *s_red = nullptr;
     double *s_ahyd = nullptr, *s_dkdt = nullptr, *s_sumvdw = nullptr, *s_mumax = nullptr;   // views into s_red
     // walk results [rank][4][walk_chunk]: tiles of 128 targets are dealt round-robin to the ranks (load balance), each
@@ -201,15 +212,14 @@ struct sph_handle {
     size_t scratch_bytes = 0;
     // timing
     cudaEvent_t ev[PH_COUNT + 1]{};
-    cudaEvent_t cev[6]{};   // begin/end of the three collectives
+    cudaEvent_t cev[8]{};   // begin/end of the four collectives of an evaluation
     cudaEvent_t wev[2]{};   // the walk kernel alone
     // the force kernel (+ its all-reduce) runs on a second stream, concurrently with the tree walk: both only need
     // the density/EOS results, and the latency-bound force kernel fills the issue slots the walk's tail leaves idle
     cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, fev[2]{}, dev[2]{};   // fev / dev: force and density phases on the stream they ran on
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, fev[2]{};   // fev: force phase on the stream it ran on
     void *nccl2 = nullptr;  // communicator of stream2 (NCCL calls of one communicator must not run concurrently)
     bool overlap = true;
-    bool density_overlapped = false;   // last evaluation ran density + EOS on stream2 as well (single GPU)
     bool ev_valid = false;
     // multi-GPU
     int nranks = 1, rank = 0;
@@ -218,8 +228,8 @@ struct sph_handle {
 };
 
 // scal[0..SC_RESET) is cleared at the start of every force evaluation; SC_STICKY accumulates error flags
-enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_KNN_RETRY, SC_RESET = 15, SC_STICKY = 15, SC_COUNT = 16 };
-enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4, ERRF_NAN = 8 };
+enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_KNN_RETRY, SC_OVF, SC_OUTBOX, SC_RESET = 15, SC_STICKY = 15, SC_COUNT = 16 };
+enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4, ERRF_NAN = 8, ERRF_EXTRAS = 16, ERRF_HALO = 32 };
 
 int sph_fail(sph_handle *h, int code, const std::string &msg);
 // cumulative count of kernel launches issued by the library in this process (bench.py's gpu_launches)
@@ -254,9 +264,12 @@ cudaError_t sph_launch_export_neighbors(sph_handle *h, int *idx_out_dev, double 
 cudaError_t sph_launch_knn_points(sph_handle *h, const double *pts_dev, int64_t M, double *d2s_dev /* M x K scratch */, double *rho_out_dev);
 
 // ---- hydro.cu ------------------------------------------------------------------------------------
-cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1);
-cudaError_t sph_launch_eos(sph_handle *h, bool write_h);
-cudaError_t sph_launch_smoothing(sph_handle *h);   // pos4.w = h from the K-th distances (before the density)
+cudaError_t sph_launch_smoothing(sph_handle *h);                          // pos4.w = d2k of ALL particles, extras table cleared
+cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1);     // rho_s + extras of the targets [t0, t1)
+cudaError_t sph_launch_outbox_header(sph_handle *h);
+cudaError_t sph_launch_extras_merge(sph_handle *h, int64_t t0, int64_t t1);
+cudaError_t sph_launch_extras_sort(sph_handle *h, int64_t t0, int64_t t1);
+cudaError_t sph_launch_eos(sph_handle *h);                                 // hr, pc, pos4.w = h of ALL particles
 cudaError_t sph_launch_force(sph_handle *h, int64_t t0, int64_t t1);
 
 // ---- gravity.cu ----------------------------------------------------------------------------------

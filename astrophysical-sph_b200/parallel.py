@@ -2,27 +2,40 @@
 
 Every rank holds the full particle state; after the key sort each rank owns one contiguous chunk of the sorted
 order (a Morton/octant-key range) as TARGETS of search / density / force / tree walk, and NCCL all-gathers
-(h, rho, g, PHI, row reductions) plus one all-reduce (hydro reactions that land on other ranks' particles)
-rebuild the replicated state.  The arithmetic here must stay identical to eval_internal() in csrc/sph_api.cu.
+(K-th distances, rho, cross-rank reverse pairs, force outputs, g, PHI) rebuild the replicated state; nothing is
+reduced across ranks.  The arithmetic here must stay identical to set_partition() in csrc/sph_api.cu.
 """
 from __future__ import annotations
 
-PAD_QUANTUM = 1680   # divisible by 1..8, 10, 12, 14, 15, 16 (csrc/sph_api.cu: sph_create)
+TILE = 128            # targets per rank are a multiple of the 128-target tiles (csrc/sph_api.cu: set_partition)
+MAX_RANKS = 16
 
 
-def padded_size(N: int) -> int:
-    return (N + PAD_QUANTUM - 1) // PAD_QUANTUM * PAD_QUANTUM
+def chunk_size(N: int, nranks: int) -> int:
+    """Targets per rank: ceil(N / nranks) rounded up to a multiple of 128."""
+    if not 1 <= nranks <= MAX_RANKS:
+        raise ValueError("unsupported rank count (1..16)")
+    per = (N + nranks - 1) // nranks
+    return (per + TILE - 1) // TILE * TILE
+
+
+def padded_size(N: int, nranks: int = 1) -> int:
+    """Stride of the sorted-space component arrays: nranks * chunk."""
+    return chunk_size(N, nranks) * nranks
 
 
 def target_range(N: int, nranks: int, rank: int) -> tuple[int, int]:
     """[t0, t1) of sorted slots owned by `rank`."""
-    NS = padded_size(N)
-    if NS % nranks:
-        raise ValueError("unsupported rank count (use 1-8, 10, 12, 14, 15 or 16)")
-    chunk = NS // nranks
+    chunk = chunk_size(N, nranks)
     t0 = min(rank * chunk, N)
-    t1 = min(t0 + chunk, N) if rank * chunk < N else N
     return t0, max(t0, min((rank + 1) * chunk, N))
+
+
+def upload_slice(N: int, nranks: int, rank: int) -> tuple[int, int]:
+    """Rows [r0, r1) of every state column that `rank` moves over PCIe in sph_upload (csrc/sph_api.cu)."""
+    per = (N + nranks - 1) // nranks
+    r0 = min(rank * per, N)
+    return r0, min(r0 + per, N)
 
 
 def share_unique_id(dist, make_id, src: int = 0) -> bytes:

@@ -116,7 +116,9 @@ int sph_synchronize(sph_handle *h);
 
 /* ---- state --------------------------------------------------------------------------------------- */
 /* Host -> device: pos, vel (N x 3 column-major), K (N, polytropic only, else NULL), time t.
- * Replaces read_snapshot's hand-over at F/isothermal_sim.jl:78-85 / F/polytrope_sim.jl:116-117. */
+ * Replaces read_snapshot's hand-over at F/isothermal_sim.jl:78-85 / F/polytrope_sim.jl:116-117.
+ * On a handle that joined a communicator this is a COLLECTIVE call: every rank passes the same arrays, moves only its
+ * 1/nranks slice of them over PCIe and the ranks exchange the slices over NVLink. */
 int sph_upload(sph_handle *h, const double *pos, const double *vel, const double *K_or_null, double t);
 /* Device -> host in the caller's particle order (any pointer may be NULL). */
 int sph_download(sph_handle *h, double *pos, double *vel, double *K_or_null, double *t);
@@ -163,8 +165,10 @@ int sph_density_at(sph_handle *h, const double *pts, int64_t M, double *rho_out)
 /* ---- multi-GPU (one process per GPU; the reference is single-process) ---------------- */
 /* 128-byte NCCL unique id, created on rank 0 and distributed by the host (torch.distributed / MPI). */
 int sph_comm_unique_id(void *id128);
-/* Join a communicator of nranks handles.  Afterwards every rank holds the full state; the targets of
- * search / density / force / walk are split by Morton-key range and exchanged with NCCL all-gathers. */
+/* Join a communicator of nranks (<= 16) handles.  Afterwards every rank holds the full state; the targets of
+ * search / density / force / walk are split by Morton-key range and the results exchanged with NCCL all-gathers
+ * (nothing is reduced across ranks: the force is evaluated in gather form).  sph_upload, sph_eval_*, sph_step and the
+ * sph_get_* calls are then collective: every rank must make the same calls in the same order. */
 int sph_comm_init(sph_handle *h, int nranks, int rank, const void *id128);
 
 #ifdef __cplusplus

@@ -109,17 +109,22 @@ def test_generate_writes_reference_layout(tmp_path):
 
 
 def test_target_ranges_tile_the_sorted_order():
-    from astrophysical_sph_b200.parallel import padded_size, target_range
+    from astrophysical_sph_b200.parallel import chunk_size, padded_size, target_range, upload_slice
 
-    for N in (64, 1000, 1679, 1680, 1681, 1_000_000, 16_000_000):
-        assert padded_size(N) % 1680 == 0 and 0 <= padded_size(N) - N < 1680
-        for P in (1, 2, 3, 4, 5, 6, 7, 8, 16):
+    for N in (64, 1000, 1679, 1680, 1681, 100_003, 1_000_000, 16_000_000):
+        for P in (1, 2, 3, 4, 5, 6, 7, 8, 9, 16):
+            c = chunk_size(N, P)
+            assert c % 128 == 0 and c * P >= N and padded_size(N, P) == c * P
+            assert padded_size(N, P) <= (N + 127) // 128 * 128 + 128 * 16      # NS_alloc of sph_create
             r = [target_range(N, P, k) for k in range(P)]
             assert r[0][0] == 0 and r[-1][1] == N
             assert all(r[i][1] == r[i + 1][0] for i in range(P - 1))
-            assert max(b - a for a, b in r) <= padded_size(N) // P
+            assert all(a % 128 == 0 for a, _ in r if a < N)                    # list tiles never straddle ranks
+            assert max(b - a for a, b in r) <= c
+            u = [upload_slice(N, P, k) for k in range(P)]
+            assert u[0][0] == 0 and u[-1][1] == N and all(u[i][1] == u[i + 1][0] for i in range(P - 1))
     with pytest.raises(ValueError):
-        target_range(1000, 9, 0)
+        target_range(1000, 17, 0)
 
 
 _GLOO_WORKER = r"""

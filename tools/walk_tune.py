@@ -48,6 +48,8 @@ def child(N, tag):
         np.savez(ref, g=g, phi=phi)
     print("%-44s grav_ms %s  kernel_ms %s  visits/particle %.2f%s" % (tag, " ".join("%.3f" % x for x in ms), " ".join("%.3f" % x for x in km), tm["walk_visits"] / N, dev),
           flush=True)
+    print("%-44s   sort %.3f tree %.3f knn %.3f density %.3f force %.3f finish %.3f total %.3f" % ("", tm["sort_ms"], tm["tree_ms"], tm["knn_ms"],
+          tm["density_ms"], tm["force_ms"], tm["finish_ms"], tm["total_ms"]), flush=True)
 
 
 if __name__ == "__main__":
