@@ -96,7 +96,8 @@ __device__ __forceinline__ int walk_root_near(const double4 *__restrict__ W, int
 
 template <bool COUNT>
 __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int nranks, int rank, int64_t chunk,
-                                                                 const double4 *__restrict__ pos4, SphTree t,
+                                                                 const double4 *__restrict__ pos4,
+                                                                 const double2 *__restrict__ hr, SphTree t,
                                                                  double theta_sq, double m,
                                                                  unsigned long long *__restrict__ scal,
                                                                  double *__restrict__ part /* [8][4][chunk] */) {
@@ -112,8 +113,8 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int n
     const bool active = s < N;
     double px = 0, py = 0, pz = 0, hi = 1.0;
     if (active) {
-        const double4 p = pos4[s];  // .w = h_i
-        px = p.x; py = p.y; pz = p.z; hi = p.w;
+        const double4 p = pos4[s];
+        px = p.x; py = p.y; pz = p.z; hi = hr[s].x;
     }
     const double hi2 = hi * hi;
     const double h2x = 2.0 * hi * (1.0 + 1e-9);      // clause 2 is certainly true when mindist > h2x
@@ -296,7 +297,8 @@ __device__ __forceinline__ void leaf_pair(double d_sq, double hi, double hj, dou
 
 template <bool COUNT>
 __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N, int nranks, int rank, int64_t chunk,
-                                                                       const double4 *__restrict__ pos4, SphTree t,
+                                                                       const double4 *__restrict__ pos4,
+                                                                       const double2 *__restrict__ hr, SphTree t,
                                                                        double theta_sq, double th_lo, double th_hi, double m,
                                                                        int sparse_t, unsigned long long *__restrict__ scal,
                                                                        double *__restrict__ part /* [8][4][chunk] */) {
@@ -312,8 +314,8 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N,
     const bool active = s < N;
     double px = 0, py = 0, pz = 0, hi = 1.0;
     if (active) {
-        const double4 p = pos4[s];  // .w = h_i
-        px = p.x; py = p.y; pz = p.z; hi = p.w;
+        const double4 p = pos4[s];
+        px = p.x; py = p.y; pz = p.z; hi = hr[s].x;
     }
     const int sbase = (int)(s - lane);               // sorted slot of lane 0's target
     const double hi2 = hi * hi;
@@ -504,14 +506,14 @@ __global__ void walk_reduce_kernel(int64_t n4 /* 4 * chunk */, int rows, const d
 }
 
 // after the search: one 64-byte walk record per node (leaves carry h_j instead of their constant mass m)
-__global__ void pack_nodes_kernel(SphTree t, const double4 *__restrict__ pos4, const unsigned long long *__restrict__ scal) {
+__global__ void pack_nodes_kernel(SphTree t, const double2 *__restrict__ hr, const unsigned long long *__restrict__ scal) {
     if (scal[SC_ERR] != 0ull) return;
     const int64_t M = (int64_t)scal[SC_NNODES];
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < M; k += (int64_t)gridDim.x * blockDim.x) {
         const int2 I = t.nodeI[k];
         double4 A = t.nodeA[k];
         double2 D = make_double2(0.0, 0.0);
-        if (I.y == 0) A.w = pos4[I.x].w;
+        if (I.y == 0) A.w = hr[I.x].x;
         else D = t.nodeD[k];
         double4 *rec = t.nodeW + GW_REC * k;
         rec[0] = A;
@@ -524,7 +526,7 @@ __global__ void pack_nodes_kernel(SphTree t, const double4 *__restrict__ pos4, c
 cudaError_t sph_launch_walk(sph_handle *h) {
     static_assert(GW_WARPS * 32 == 128, "walk tiles are 128 targets (finish_kernel and sph_comm_init assume it)");
     sph_note(1);
-    pack_nodes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->tree, h->pos4, h->scal);
+    pack_nodes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->tree, h->hr, h->scal);
     const int64_t tiles = (h->N + 127) / 128;
     const int64_t groups = (tiles + SPH_WALK_DEAL - 1) / SPH_WALK_DEAL;
     const int64_t blocks = (groups - h->rank + h->nranks - 1) / h->nranks * SPH_WALK_DEAL;   // groups rank, rank + P, ...
@@ -557,17 +559,17 @@ cudaError_t sph_launch_walk(sph_handle *h) {
     if (shared_only || h->tree.cap >= (1ll << 27) || h->N >= (1ll << 31)) {
         // the shared depth-first walk alone (SPH_B200_WALK_DFS=1, or node ids that do not fit the pair encoding)
         if (count)
-            walk_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+            walk_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree,
                                                                      th2, h->p.m, h->scal, part);
         else
-            walk_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+            walk_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree,
                                                                       th2, h->p.m, h->scal, part);
     } else {
         if (count)
-            walk_pairs_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+            walk_pairs_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree,
                                                                            th2, th2 * (1.0 - 1e-15), th2 * (1.0 + 1e-15), h->p.m, sparse_t, h->scal, part);
         else
-            walk_pairs_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->tree,
+            walk_pairs_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree,
                                                                             th2, th2 * (1.0 - 1e-15), th2 * (1.0 + 1e-15), h->p.m, sparse_t, h->scal, part);
     }
     cudaEventRecord(h->wev[1], h->stream);

@@ -5,7 +5,7 @@
 // evolve_K! (F/isothermal_hydroKDTree.jl:5-245, F/polytrope_hydroKDTree.jl:5-341).  The reference
 // materialises ~35 N x K Float64 matrices per call; here every pair quantity lives in registers and only
 // the per-particle reductions its caller consumes are written:
-//   rho, h, P/rho^2, c_i                                       (density + EOS)
+//   rho, h, P/rho^2, c_i                                       (density + EOS; pos4.w carries d2k = (2h)^2 throughout)
 //   a_hyd, sum_j v_ij.gradW_ij, max_j mu_ij, dK/dt sum         (force)
 //
 // The reference's pair loop is a scatter (F/isothermal_hydroKDTree.jl:226-242): for j in N(i), j != i:
@@ -119,19 +119,40 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 
 // ---------------------------------------------------------------------------------------------------
-// density + extras pass.  pos4.w holds d2k (the K-th squared distance of every particle) during this pass.
+// density + extras pass.  pos4.w holds d2k (the K-th squared distance of every particle).
 // TILE: the block's K x 128 list tile and the records of the key-order window [tile - TW, tile + 128 + TW) are staged
 // in shared memory by bulk async copies; neighbours outside the window are gathered from global memory.
 // ---------------------------------------------------------------------------------------------------
 constexpr int TW = 128;                 // window margin on each side of the 128-target tile
 constexpr int TWIN = HB + 2 * TW;       // records in the window
 
-template <bool TILE>
+// EOS closure of one particle: isothermal P = cs^2 rho (F/isothermal_hydroKDTree.jl:190), c = cs; polytropic
+// P = K rho^gamma (F/polytrope_hydroKDTree.jl:216), c_i = sqrt(gamma K rho^(gamma-1)) (:186).
+// hr = {h, rho}; pc = {rho, P/rho^2, h, c}: the 32-byte record the force pass gathers per neighbour.
+__device__ __forceinline__ void eos_store(int64_t s, double h, double rho, double Kent, int poly, double cs, double gamma,
+                                          double2 *__restrict__ hr, double4 *__restrict__ pc) {
+    double P, c;
+    if (!poly) {
+        P = cs * cs * rho;
+        c = cs;
+    } else {
+        c = sqrt(gamma * Kent * pow(rho, gamma - 1));
+        P = Kent * pow(rho, gamma);
+    }
+    hr[s] = make_double2(h, rho);
+    pc[s] = make_double4(rho, P / (rho * rho), h, c);
+}
+
+// EOS: with one rank the density pass closes the EOS of its target on the spot (every particle is a target);
+// with several ranks rho is all-gathered first and eos_kernel runs over all particles.
+template <bool TILE, bool EOS>
 __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int K, int64_t t0, int64_t t1,
                                                       const double4 *__restrict__ pos4, const int *__restrict__ nbr,
                                                       const int *__restrict__ perm, const int *__restrict__ kid,
                                                       double m, int poly, unsigned long long *__restrict__ scal,
-                                                      ExtrasOut x, double *__restrict__ rho_out) {
+                                                      ExtrasOut x, double *__restrict__ rho_out,
+                                                      const double4 *__restrict__ vel4, double cs, double gamma,
+                                                      double2 *__restrict__ hr, double4 *__restrict__ pc) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     if (scal[SC_ERR] != 0ull) return;
     const int64_t s0 = t0 + (int64_t)blockIdx.x * HB;
@@ -189,7 +210,8 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int 
             if (!in_list_of(d2, pj.w, (int)s, nj, perm, kid)) push_extra(x, nj, (int)s, scal);
         }
     }
-    rho_out[s] = m * sum;
+    if (EOS) eos_store(s, h, m * sum, poly ? vel4[s].w : 0.0, poly, cs, gamma, hr, pc);
+    else rho_out[s] = m * sum;
 }
 
 // extras of other ranks' targets that point into this rank's range: append them (order is fixed afterwards)
@@ -212,66 +234,28 @@ __global__ void outbox_header_kernel(int2 *__restrict__ outbox, int obcap, const
     outbox[0] = make_int2((int)(n < (unsigned long long)obcap ? n : (unsigned long long)obcap), 0);
 }
 
-// fixed order of every particle's extras (slots were handed out by atomics): ascending sorted-space index
-__global__ void __launch_bounds__(HB) extras_sort_kernel(int64_t NL, int64_t t0, int64_t t1, int ecap,
-                                                          const int *__restrict__ ecnt, int *__restrict__ ext,
-                                                          const unsigned long long *__restrict__ scal) {
-    if (scal[SC_ERR] != 0ull) return;
-    const int64_t s = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= t1) return;
-    int n = ecnt[s];
-    n = n < ecap ? n : ecap;
-    for (int a = 0; a + 1 < n; ++a) {              // selection sort on the column of this particle (n is ~4)
-        int best = ext[(int64_t)a * NL + s], bi = a;
-        for (int b = a + 1; b < n; ++b) {
-            const int v = ext[(int64_t)b * NL + s];
-            if (v < best) { best = v; bi = b; }
-        }
-        if (bi != a) {
-            ext[(int64_t)bi * NL + s] = ext[(int64_t)a * NL + s];
-            ext[(int64_t)a * NL + s] = best;
-        }
-    }
-}
-
-// EOS closure for ALL particles (after the density all-gather in multi-GPU runs):
-//   isothermal  P = cs^2 rho (F/isothermal_hydroKDTree.jl:190), c = cs
-//   polytropic  P = K rho^gamma (F/polytrope_hydroKDTree.jl:216), c_i = sqrt(gamma K rho^(gamma-1)) (:186)
-// writes hr = {h, rho}, pc = {rho, P/rho^2, d2k, c} (one 32-byte record per gathered neighbour in the force pass)
-// and turns pos4.w from d2k into h (leaf softening of the tree walk, pair averages of the force).
-__global__ void __launch_bounds__(HB) eos_kernel(int64_t N, const double *__restrict__ rho_s,
+// EOS closure for ALL particles after the density all-gather of multi-GPU runs (pos4.w = d2k)
+__global__ void __launch_bounds__(HB) eos_kernel(int64_t N, const double *__restrict__ rho_s, const double4 *__restrict__ pos4,
                                                   const double4 *__restrict__ vel4, int poly, double cs, double gamma,
                                                   const unsigned long long *__restrict__ scal, double2 *__restrict__ hr,
-                                                  double4 *__restrict__ pc, double4 *__restrict__ pos4) {
+                                                  double4 *__restrict__ pc) {
     if (scal[SC_ERR] != 0ull) return;
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
-    const double rho = rho_s[s];
-    const double d2k = pos4[s].w;
-    const double h = sqrt(d2k) / 2;                  // h = r[:, end] ./ 2   (:151)
-    double P, c;
-    if (!poly) {
-        P = cs * cs * rho;
-        c = cs;
-    } else {
-        const double Kent = vel4[s].w;
-        c = sqrt(gamma * Kent * pow(rho, gamma - 1));
-        P = Kent * pow(rho, gamma);
-    }
-    hr[s] = make_double2(h, rho);
-    pc[s] = make_double4(rho, P / (rho * rho), d2k, c);
-    pos4[s].w = h;
+    const double h = sqrt(pos4[s].w) / 2;            // h = r[:, end] ./ 2   (:151)
+    eos_store(s, h, rho_s[s], poly ? vel4[s].w : 0.0, poly, cs, gamma, hr, pc);
 }
 
-// pos4.w = d2k for ALL particles (after the d2k all-gather in multi-GPU runs): the density pass reads the K-th
-// distance of every neighbour next to its position
+// pos4.w = d2k for ALL particles (after the d2k all-gather in multi-GPU runs): the density and force passes read the
+// K-th distance of every neighbour next to its position; also clears the extras counters
 __global__ void __launch_bounds__(HB) smoothing_kernel(int64_t N, const double *__restrict__ d2k,
                                                         const unsigned long long *__restrict__ scal,
-                                                        double4 *__restrict__ pos4) {
+                                                        double4 *__restrict__ pos4, int *__restrict__ ecnt) {
     if (scal[SC_ERR] != 0ull) return;
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
     pos4[s].w = d2k[s];
+    ecnt[s] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -291,7 +275,7 @@ __device__ __forceinline__ void pair_terms(const Target &t, const double4 &pj, c
     const double d2 = sph_d2_exact(dx, dy, dz);
     const double rinv = d2 > 0.0 ? fast_rsqrt(d2) : 0.0;
     const double r = d2 * rinv;
-    const double h_avg = (t.h + pj.w) / 2;                                   // getVectorTreeAvgs (:111)
+    const double h_avg = (t.h + cj.z) / 2;                                   // getVectorTreeAvgs (:111)
     const double rho_avg = (t.rho + cj.x) / 2;
     const double vx = t.vx - vj.x, vy = t.vy - vj.y, vz = t.vz - vj.z;
     const double vdr = (vx * dx + vy * dy) + vz * dz;                        // (:210)
@@ -313,7 +297,7 @@ __device__ __forceinline__ void pair_terms(const Target &t, const double4 &pj, c
         if (POLY) dk += m * Pi * vdw / 2;                                    // evolve_K! poly :305-311
     }
     if (rev) {
-        const double hinv_j = fast_rcp(pj.w);
+        const double hinv_j = fast_rcp(cj.z);
         const double hi2 = hinv_j * hinv_j;
         const double ct4_j = INV_PI_D * (hi2 * hi2);                         // 1 / (pi h_j^4)
         const double q = r * hinv_j;
@@ -379,7 +363,7 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int6
         const double4 pi = TILE ? wpos[s - w0] : pos4[s];
         const double4 vi = TILE ? wvel[s - w0] : vel4[s];
         const double4 ci = TILE ? wpc[s - w0] : pc[s];
-        t.x = pi.x; t.y = pi.y; t.z = pi.z; t.h = pi.w;
+        t.x = pi.x; t.y = pi.y; t.z = pi.z; t.h = ci.z;
         t.vx = vi.x; t.vy = vi.y; t.vz = vi.z;
         t.rho = ci.x; t.prr = ci.y; t.cs = ci.w;
         const double h2 = t.h * t.h;
@@ -406,15 +390,22 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int6
         }
         // does nj's list contain s?  then its reaction on s is gathered here (mutual pair)
         const double d2 = sph_d2_exact(t.x - pj.x, t.y - pj.y, t.z - pj.z);
-        const bool rev = in_list_of(d2, cj.z, (int)s, nj, perm, kid);
+        const bool rev = in_list_of(d2, pj.w, (int)s, nj, perm, kid);
         pair_terms<POLY, true>(t, pj, vj, cj, rev, m, alpha, beta, ax, ay, az, dk, svdw, mmax);
     }
-    // reverse partners outside the own list, ascending index
+    // reverse partners outside the own list (3.7 on average), in ascending index order whatever slots the atomics of
+    // the density pass handed out: the next one is selected by a scan of the particle's column
     int ne = ecnt[s];
     ne = ne < ecap ? ne : ecap;
     double dummy_s = 0.0, dummy_m = 0.0;
+    int last = -1;
     for (int e = 0; e < ne; ++e) {
-        const int k = ext[(int64_t)e * NL + s];
+        int k = 0x7fffffff;
+        for (int b = 0; b < ne; ++b) {
+            const int v = ext[(int64_t)b * NL + s];
+            if (v > last && v < k) k = v;
+        }
+        last = k;
         const double4 pj = pos4[k], vj = vel4[k], cj = pc[k];
         pair_terms<POLY, false>(t, pj, vj, cj, true, m, alpha, beta, ax, ay, az, dk, dummy_s, dummy_m);
     }
@@ -442,7 +433,7 @@ __global__ void __launch_bounds__(HB) force_overflow_kernel(int64_t NS, int64_t 
     Target t;
     {
         const double4 pi = pos4[s], vi = vel4[s], ci = pc[s];
-        t.x = pi.x; t.y = pi.y; t.z = pi.z; t.h = pi.w;
+        t.x = pi.x; t.y = pi.y; t.z = pi.z; t.h = ci.z;
         t.vx = vi.x; t.vy = vi.y; t.vz = vi.z;
         t.rho = ci.x; t.prr = ci.y; t.cs = ci.w;
         t.ct4 = 0.0; t.hinv = 0.0;
@@ -488,34 +479,42 @@ static bool use_tile_kernels() {
 
 cudaError_t sph_launch_smoothing(sph_handle *h) {
     sph_note(1);
-    cudaMemsetAsync(h->ecnt, 0, sizeof(int) * (size_t)h->NL, h->stream);
-    smoothing_kernel<<<(int)((h->N + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->d2k, h->scal, h->pos4);
+    smoothing_kernel<<<(int)((h->N + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->d2k, h->scal, h->pos4, h->ecnt);
     return cudaGetLastError();
 }
 
-cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1) {
-    if (t1 <= t0) return cudaSuccess;
-    sph_note(1);
+template <bool EOS>
+static cudaError_t launch_density(sph_handle *h, int64_t t0, int64_t t1) {
     const int64_t nt = t1 - t0;
     const int blocks = (int)((nt + HB - 1) / HB);
     const ExtrasOut x = extras_of(h, t0, t1);
     const int poly = h->p.eos == SPH_EOS_POLYTROPIC;
-    // the tile kernels need 16-byte aligned list tiles: t0 is a multiple of 128 (sph_comm_init) and NL of 128
+    // the tile kernels need 16-byte aligned list tiles: t0 is a multiple of 128 (set_partition) and so is NL
     if (use_tile_kernels() && (t0 % HB) == 0) {
         const size_t smem = DENS_SMEM + (size_t)h->K * HB * sizeof(int);
         static bool attr = false;
         if (!attr) {
-            cudaError_t e = cudaFuncSetAttribute(density_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(density_kernel<true, EOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
             if (e != cudaSuccess) return e;
             attr = true;
         }
-        density_kernel<true><<<blocks, HB, smem, h->stream>>>(h->N, h->NL, h->K, t0, t1, h->pos4, h->nbr, h->perm, h->kid,
-                                                              h->p.m, poly, h->scal, x, h->rho_s);
+        density_kernel<true, EOS><<<blocks, HB, smem, h->stream>>>(h->N, h->NL, h->K, t0, t1, h->pos4, h->nbr, h->perm, h->kid,
+                                                                   h->p.m, poly, h->scal, x, h->rho_s, h->vel4, h->p.cs, h->p.gamma,
+                                                                   h->hr, h->pc);
     } else {
-        density_kernel<false><<<blocks, HB, 0, h->stream>>>(h->N, h->NL, h->K, t0, t1, h->pos4, h->nbr, h->perm, h->kid,
-                                                            h->p.m, poly, h->scal, x, h->rho_s);
+        density_kernel<false, EOS><<<blocks, HB, 0, h->stream>>>(h->N, h->NL, h->K, t0, t1, h->pos4, h->nbr, h->perm, h->kid,
+                                                                 h->p.m, poly, h->scal, x, h->rho_s, h->vel4, h->p.cs, h->p.gamma,
+                                                                 h->hr, h->pc);
     }
     return cudaGetLastError();
+}
+
+// with_eos: one rank - the EOS of every target is closed in the same kernel (hr, pc written); several ranks - only
+// rho_s of the owned targets, sph_launch_eos follows the all-gather
+cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1, bool with_eos) {
+    if (t1 <= t0) return cudaSuccess;
+    sph_note(1);
+    return with_eos ? launch_density<true>(h, t0, t1) : launch_density<false>(h, t0, t1);
 }
 
 cudaError_t sph_launch_outbox_header(sph_handle *h) {
@@ -530,17 +529,10 @@ cudaError_t sph_launch_extras_merge(sph_handle *h, int64_t t0, int64_t t1) {
     return cudaGetLastError();
 }
 
-cudaError_t sph_launch_extras_sort(sph_handle *h, int64_t t0, int64_t t1) {
-    if (t1 <= t0) return cudaSuccess;
-    sph_note(1);
-    extras_sort_kernel<<<(int)((t1 - t0 + HB - 1) / HB), HB, 0, h->stream>>>(h->NL, t0, t1, h->ecap, h->ecnt, h->ext, h->scal);
-    return cudaGetLastError();
-}
-
 cudaError_t sph_launch_eos(sph_handle *h) {
     sph_note(1);
-    eos_kernel<<<(int)((h->N + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->rho_s, h->vel4, h->p.eos == SPH_EOS_POLYTROPIC,
-                                                                  h->p.cs, h->p.gamma, h->scal, h->hr, h->pc, h->pos4);
+    eos_kernel<<<(int)((h->N + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->rho_s, h->pos4, h->vel4, h->p.eos == SPH_EOS_POLYTROPIC,
+                                                                  h->p.cs, h->p.gamma, h->scal, h->hr, h->pc);
     return cudaGetLastError();
 }
 

@@ -194,7 +194,7 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
         SPH_CUDA(h, cudaEventRecord(h->cev[1], st));
     }
     SPH_CUDA(h, sph_launch_smoothing(h));
-    SPH_CUDA(h, sph_launch_density(h, t0, t1));
+    SPH_CUDA(h, sph_launch_density(h, t0, t1, !multi));
     TRACE("sph_launch_density done");
     if (multi) {   // rho of all particles; reverse pairs that point at other ranks' targets
         SPH_CUDA(h, sph_launch_outbox_header(h));
@@ -205,10 +205,9 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
         SPH_NCCL(h, nc.GroupEnd());
         SPH_CUDA(h, cudaEventRecord(h->cev[3], st));
         SPH_CUDA(h, sph_launch_extras_merge(h, t0, t1));
+        SPH_CUDA(h, sph_launch_eos(h));
+        TRACE("sph_launch_eos done");
     }
-    SPH_CUDA(h, sph_launch_eos(h));
-    SPH_CUDA(h, sph_launch_extras_sort(h, t0, t1));
-    TRACE("sph_launch_eos done");
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_DENSITY + 1], st));
     // ---- force (second stream when overlapping) || walk (main stream)
     const bool ov = h->overlap && (!multi || h->nccl2 != nullptr);
