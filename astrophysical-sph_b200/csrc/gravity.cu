@@ -22,7 +22,8 @@
 namespace {
 
 constexpr int GW_WARPS = 4;
-constexpr int GW_STACK = 192;
+constexpr int GW_STACK = 192;          // shared stack of the walks: 7 pending siblings per level + 8 covers 26 levels
+constexpr int GW_STACK_DEEP = 304;     // ... and all 42 levels (7 * 42 + 8): the DEEP variants, see sph_launch_walk
 constexpr int GW_REC = SPH_WALK_REC;   // double4 per walk record: {rCOM, Mass | h_j}, {(2L)^2, radius, child info, range}
 
 // coefficients of the softened kernels below, read as constant-bank operands (as literals each one costs two
@@ -94,15 +95,24 @@ __device__ __forceinline__ int walk_root_near(const double4 *__restrict__ W, int
     return near;
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int nranks, int rank, int64_t chunk,
+// true: this launch has nothing to do.  The regular variants run unless an error is flagged; the DEEP variants run only
+// when the regular walk of this evaluation overflowed its stack (and nothing else went wrong) and redo every tile.
+template <bool DEEP>
+__device__ __forceinline__ bool walk_skipped(const unsigned long long *__restrict__ scal) {
+    const unsigned long long f = scal[SC_ERR];
+    return DEEP ? f != (unsigned long long)ERRF_STACK : f != 0ull;
+}
+
+template <bool COUNT, bool DEEP>
+__global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : 8) walk_kernel(int64_t N, int nranks, int rank, int64_t chunk,
                                                                  const double4 *__restrict__ pos4,
                                                                  const double2 *__restrict__ hr, SphTree t,
                                                                  double theta_sq, double m,
                                                                  unsigned long long *__restrict__ scal,
                                                                  double *__restrict__ part /* [8][4][chunk] */) {
-    __shared__ int4 s_stack[GW_WARPS][GW_STACK];   // {first child, nch | leafmask << 8, lane mask, -}
-    if (scal[SC_ERR] != 0ull) return;
+    constexpr int STACK = DEEP ? GW_STACK_DEEP : GW_STACK;
+    __shared__ int4 s_stack[GW_WARPS][STACK];   // {first child, nch | leafmask << 8, lane mask, -}
+    if (walk_skipped<DEEP>(scal)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int4 *stack = s_stack[warp];
     const double4 *__restrict__ W = t.nodeW;
@@ -148,8 +158,8 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int n
         __syncwarp();
         const bool mine = (((unsigned)top.z) >> lane) & 1u;
         const int first = top.x, nch = top.y & 0xff, leafmask = top.y >> 8;
-        if (sp + nch > GW_STACK) {  // cannot happen for depth <= 21; never write out of bounds
-            if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)ERRF_STACK);
+        if (sp + nch > STACK) {     // never write out of bounds: the DEEP variant redoes the walk (it cannot overflow)
+            if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)(DEEP ? ERRF_STACK2 : ERRF_STACK));
             break;
         }
 #pragma unroll 1
@@ -243,19 +253,24 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_kernel(int64_t N, int n
 // memory; pairs of one round that belong to the same target are serialised by their lane rank, so the sums
 // are deterministic.  The set of (particle, node) visits - hence every decision - is the one of the
 // reference; only the summation order differs.
-// The queue can never overflow: a round pops B <= (SOFT - qn) / 7 pairs (each pushes at most 8 children);
-// B = 1 is a depth-first descent whose excursion is bounded by 7 * 21 + 8 entries (the slack above SOFT),
-// and cells are only expanded into the queue while it holds < 32 pairs.
+// The queue cannot overflow in a tree of up to 21 levels: a round pops B <= (SOFT - qn) / 7 pairs (each pushes at most 8
+// children); B = 1 is a depth-first descent whose excursion is bounded by 7 per level + 8 entries (the slack above
+// SOFT), and cells are only expanded into the queue while it holds < 32 pairs.  Deeper trees (two-word keys, up to 42
+// levels) almost never need more - single-child chains do not grow a stack - but the bound no longer holds, so stack
+// and queue are guarded: an overflow raises ERRF_STACK and sph_launch_walk's DEEP variant (sized for 42 levels, half
+// the occupancy) redoes the walk of this evaluation.
 // ---------------------------------------------------------------------------------------------------
 constexpr int GP_TMAX = 16;              // cells with <= sparse_t <= GP_TMAX interested lanes go to the pair queue
-constexpr int GP_STACK = 160;            // shared stack of dense cells: 7 per level + 8
+constexpr int GP_STACK = 160;            // shared stack of dense cells: 7 per level + 8 covers 21 levels
 constexpr int GP_SOFT = 352;
-constexpr int GP_CAP = GP_SOFT + 160;
+constexpr int GP_SLACK = 160;            // depth-first excursion of the queue above GP_SOFT: 7 per level + 8
+constexpr int GP_DEEP = 304;             // both, for all 42 levels (DEEP variant)
 
+template <int STACK, int SLACK>
 struct GpWarp {
-    int2 stack[GP_STACK];                // {first child | nch << 27, lane mask}
+    int2 stack[STACK];                   // {first child | nch << 27, lane mask}
     double4 acc[32];                     // sparse-path sums {gx, gy, gz, phi} of the warp's 32 targets
-    int q[GP_CAP];                       // pairs: node | target lane << 27
+    int q[GP_SOFT + SLACK];              // pairs: node | target lane << 27
 };
 
 // the reference's acceptance rule (:265) for one particle and one internal cell: same arithmetic as walk_kernel
@@ -295,18 +310,19 @@ __device__ __forceinline__ void leaf_pair(double d_sq, double hi, double hj, dou
     }
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N, int nranks, int rank, int64_t chunk,
+template <bool COUNT, bool DEEP>
+__global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : 8) walk_pairs_kernel(int64_t N, int nranks, int rank, int64_t chunk,
                                                                        const double4 *__restrict__ pos4,
                                                                        const double2 *__restrict__ hr, SphTree t,
                                                                        double theta_sq, double th_lo, double th_hi, double m,
                                                                        int sparse_t, unsigned long long *__restrict__ scal,
                                                                        double *__restrict__ part /* [8][4][chunk] */) {
-    __shared__ GpWarp s_w[GW_WARPS];
-    if (scal[SC_ERR] != 0ull) return;
+    constexpr int STACK = DEEP ? GP_DEEP : GP_STACK, QCAP = GP_SOFT + (DEEP ? GP_DEEP : GP_SLACK);
+    __shared__ GpWarp<STACK, QCAP - GP_SOFT> s_w[GW_WARPS];
+    if (walk_skipped<DEEP>(scal)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    GpWarp &sm = s_w[warp];
+    GpWarp<STACK, QCAP - GP_SOFT> &sm = s_w[warp];
     const double4 *__restrict__ W = t.nodeW;
     const int64_t local = (int64_t)blockIdx.x * (GW_WARPS * 32) + threadIdx.x;
     const int64_t gtile = ((int64_t)(blockIdx.x / SPH_WALK_DEAL) * nranks + rank) * SPH_WALK_DEAL + blockIdx.x % SPH_WALK_DEAL;
@@ -397,6 +413,11 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N,
                     if (lane >= o) off += a;
                 }
                 const int total = __shfl_sync(0xffffffffu, off, 31);
+                if (qn + total > QCAP) {       // only in trees deeper than 21 levels: the DEEP variant takes over
+                    if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)(DEEP ? ERRF_STACK2 : ERRF_STACK));
+                    sp = 0; qn = 0;
+                    continue;
+                }
                 int *dst = sm.q + (qn + off - cn);
                 const unsigned tag = (unsigned)tl << 27;
 #pragma unroll 1
@@ -435,8 +456,8 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N,
             __syncwarp();
             continue;
         }
-        if (sp + nch > GP_STACK) {  // cannot happen for depth <= 21; never write out of bounds
-            if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)ERRF_STACK);
+        if (sp + nch > STACK) {     // only in trees deeper than 21 levels: the DEEP variant takes over
+            if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)(DEEP ? ERRF_STACK2 : ERRF_STACK));
             break;
         }
 #pragma unroll 1
@@ -489,6 +510,16 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 8) walk_pairs_kernel(int64_t N,
         for (int o = 16; o > 0; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
         if (lane == 0) atomicAdd(scal + SC_VISITS, visits);
     }
+}
+
+// SPH_B200_WALK_FORCE_DEEP=1 (tests): pretend the regular walk overflowed, so that the DEEP variant produces the result
+__global__ void walk_force_overflow_kernel(unsigned long long *__restrict__ scal) {
+    if (scal[SC_ERR] == 0ull) scal[SC_ERR] = (unsigned long long)ERRF_STACK;
+}
+
+// after the DEEP variant: the regular walk's overflow is dealt with
+__global__ void walk_clear_overflow_kernel(unsigned long long *__restrict__ scal) {
+    if (scal[SC_ERR] & (unsigned long long)ERRF_STACK) scal[SC_ERR] &= ~(unsigned long long)ERRF_STACK;
 }
 
 // sum of the per-row partial results in row order -> this rank's section of walk_buf
@@ -556,23 +587,29 @@ cudaError_t sph_launch_walk(sph_handle *h) {
         const int v = e ? atoi(e) : 12;
         return v < 0 ? 0 : (v > GP_TMAX ? GP_TMAX : v);
     }();
-    if (shared_only || h->tree.cap >= (1ll << 27) || h->N >= (1ll << 31)) {
-        // the shared depth-first walk alone (SPH_B200_WALK_DFS=1, or node ids that do not fit the pair encoding)
-        if (count)
-            walk_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree,
-                                                                     th2, h->p.m, h->scal, part);
-        else
-            walk_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree,
-                                                                      th2, h->p.m, h->scal, part);
-    } else {
-        if (count)
-            walk_pairs_kernel<true><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree,
-                                                                           th2, th2 * (1.0 - 1e-15), th2 * (1.0 + 1e-15), h->p.m, sparse_t, h->scal, part);
-        else
-            walk_pairs_kernel<false><<<grid, GW_WARPS * 32, 0, h->stream>>>(h->N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree,
-                                                                            th2, th2 * (1.0 - 1e-15), th2 * (1.0 + 1e-15), h->p.m, sparse_t, h->scal, part);
-    }
+    const double lo = th2 * (1.0 - 1e-15), hi = th2 * (1.0 + 1e-15);
+    const int64_t N = h->N;
+    const bool shared = shared_only || h->tree.cap >= (1ll << 27) || h->N >= (1ll << 31);   // node ids that do not fit the pair encoding
+#define WALK_LAUNCH(DEEP)                                                                                                       \
+    do {                                                                                                                        \
+        if (shared) {                                                                                                           \
+            if (count) walk_kernel<true, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree, th2, h->p.m, h->scal, part);   \
+            else walk_kernel<false, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree, th2, h->p.m, h->scal, part);        \
+        } else {                                                                                                                \
+            if (count) walk_pairs_kernel<true, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree, th2, lo, hi, h->p.m, sparse_t, h->scal, part);   \
+            else walk_pairs_kernel<false, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree, th2, lo, hi, h->p.m, sparse_t, h->scal, part);        \
+        }                                                                                                                       \
+    } while (0)
+    WALK_LAUNCH(false);
     cudaEventRecord(h->wev[1], h->stream);
+    // trees deeper than 21 levels may overflow the regular variant's stack: the DEEP variant (a no-op otherwise: its
+    // blocks leave at once) then redoes every tile with stacks sized for 42 levels
+    sph_note(2);
+    static const bool force_deep = getenv("SPH_B200_WALK_FORCE_DEEP") != nullptr;
+    if (force_deep) walk_force_overflow_kernel<<<1, 1, 0, h->stream>>>(h->scal);
+    WALK_LAUNCH(true);
+#undef WALK_LAUNCH
+    walk_clear_overflow_kernel<<<1, 1, 0, h->stream>>>(h->scal);
     if (rows > 1) {
         sph_note(1);
         walk_reduce_kernel<<<148 * 8, 256, 0, h->stream>>>(4 * h->walk_chunk, rows, h->walk_part, h->tree.nodeW, h->scal, out);

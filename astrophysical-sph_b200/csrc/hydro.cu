@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int 
     const double ct = 1 / (PI_D * (h * h * h));
     const double hinv = 1 / h;
     double sum = 0.0;
+    unsigned long long defer = 0ull;     // bit j: the j-th neighbour's list does not hold s (told after the loop)
     for (int j = 0; j < K; ++j) {
         const int nj = lst[j * lstride];
         double4 pj;
@@ -205,10 +206,20 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int 
         const double d2 = sph_d2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
         const double q = d2 > 0.0 ? d2 * fast_rsqrt(d2) * hinv : 0.0;
         sum += kernel_W(ct, q, poly != 0);           // rho_i = m * sum_j w_ij  (:175)
-        // s is in nj's list <=> nj finds s itself when it gathers; otherwise nj must be told (its extras table)
+        // s is in nj's list <=> nj finds s itself when it gathers; otherwise nj must be told (its extras table).
+        // The atomics that hand out the table slots are issued after the loop: inside it nearly every warp iteration
+        // would wait for the round trip of the one or two lanes that have something to tell.
         if (!(d2 < pj.w) && nj != (int)s) {
-            if (!in_list_of(d2, pj.w, (int)s, nj, perm, kid)) push_extra(x, nj, (int)s, scal);
+            if (!in_list_of(d2, pj.w, (int)s, nj, perm, kid)) {
+                if (j < 64) defer |= 1ull << j;
+                else push_extra(x, nj, (int)s, scal);
+            }
         }
+    }
+    while (defer) {
+        const int j = __ffsll((long long)defer) - 1;
+        defer &= defer - 1ull;
+        push_extra(x, lst[j * lstride], (int)s, scal);
     }
     if (EOS) eos_store(s, h, m * sum, poly ? vel4[s].w : 0.0, poly, cs, gamma, hr, pc);
     else rho_out[s] = m * sum;
@@ -232,6 +243,28 @@ __global__ void __launch_bounds__(256) extras_merge_kernel(const int2 *__restric
 __global__ void outbox_header_kernel(int2 *__restrict__ outbox, int obcap, const unsigned long long *__restrict__ scal) {
     const unsigned long long n = scal[SC_OUTBOX];
     outbox[0] = make_int2((int)(n < (unsigned long long)obcap ? n : (unsigned long long)obcap), 0);
+}
+
+// fixed order of every particle's extras (the slots were handed out by atomics): ascending sorted-space index
+__global__ void __launch_bounds__(HB) extras_sort_kernel(int64_t NL, int64_t t0, int64_t t1, int ecap,
+                                                          const int *__restrict__ ecnt, int *__restrict__ ext,
+                                                          const unsigned long long *__restrict__ scal) {
+    if (scal[SC_ERR] != 0ull) return;
+    const int64_t s = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= t1) return;
+    int n = ecnt[s];
+    n = n < ecap ? n : ecap;
+    for (int a = 0; a + 1 < n; ++a) {              // selection sort on the column of this particle (n is ~4)
+        int best = ext[(int64_t)a * NL + s], bi = a;
+        for (int b = a + 1; b < n; ++b) {
+            const int v = ext[(int64_t)b * NL + s];
+            if (v < best) { best = v; bi = b; }
+        }
+        if (bi != a) {
+            ext[(int64_t)bi * NL + s] = ext[(int64_t)a * NL + s];
+            ext[(int64_t)a * NL + s] = best;
+        }
+    }
 }
 
 // EOS closure for ALL particles after the density all-gather of multi-GPU runs (pos4.w = d2k)
@@ -393,19 +426,12 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int6
         const bool rev = in_list_of(d2, pj.w, (int)s, nj, perm, kid);
         pair_terms<POLY, true>(t, pj, vj, cj, rev, m, alpha, beta, ax, ay, az, dk, svdw, mmax);
     }
-    // reverse partners outside the own list (3.7 on average), in ascending index order whatever slots the atomics of
-    // the density pass handed out: the next one is selected by a scan of the particle's column
+    // reverse partners outside the own list (3.7 on average), ascending index (extras_sort_kernel)
     int ne = ecnt[s];
     ne = ne < ecap ? ne : ecap;
     double dummy_s = 0.0, dummy_m = 0.0;
-    int last = -1;
     for (int e = 0; e < ne; ++e) {
-        int k = 0x7fffffff;
-        for (int b = 0; b < ne; ++b) {
-            const int v = ext[(int64_t)b * NL + s];
-            if (v > last && v < k) k = v;
-        }
-        last = k;
+        const int k = ext[(int64_t)e * NL + s];
         const double4 pj = pos4[k], vj = vel4[k], cj = pc[k];
         pair_terms<POLY, false>(t, pj, vj, cj, true, m, alpha, beta, ax, ay, az, dk, dummy_s, dummy_m);
     }
@@ -526,6 +552,13 @@ cudaError_t sph_launch_outbox_header(sph_handle *h) {
 cudaError_t sph_launch_extras_merge(sph_handle *h, int64_t t0, int64_t t1) {
     sph_note(1);
     extras_merge_kernel<<<148 * 2, 256, 0, h->stream>>>(h->inbox, h->nranks, h->rank, h->obcap + 1, extras_of(h, t0, t1), h->scal);
+    return cudaGetLastError();
+}
+
+cudaError_t sph_launch_extras_sort(sph_handle *h, int64_t t0, int64_t t1) {
+    if (t1 <= t0) return cudaSuccess;
+    sph_note(1);
+    extras_sort_kernel<<<(int)((t1 - t0 + HB - 1) / HB), HB, 0, h->stream>>>(h->NL, t0, t1, h->ecap, h->ecnt, h->ext, h->scal);
     return cudaGetLastError();
 }
 

@@ -28,7 +28,7 @@ namespace {
 
 constexpr int KNN_WARPS = 8;
 constexpr int KNN_BUCKET = 32;
-constexpr int KNN_STACK = 192;
+constexpr int KNN_STACK = 304;   // cells to visit: 7 pending siblings per level + 8, 42 levels
 
 __device__ __forceinline__ bool cand_less(double da, int ia, double db, int ib, const int *__restrict__ perm) {
     if (da < db) return true;

@@ -92,11 +92,13 @@ __global__ void export_tree_kernel(SphTree t, const unsigned long long *__restri
 }
 
 __global__ void export_tree_centres_kernel(SphTree t, const unsigned long long *__restrict__ scal,
-                                           const uint64_t *__restrict__ keys, int64_t cap, double *__restrict__ out) {
+                                           const uint64_t *__restrict__ keys, const uint64_t *__restrict__ klo, int64_t cap,
+                                           double *__restrict__ out) {
     const int64_t M = min((int64_t)scal[SC_NNODES], cap);
     const double l = __longlong_as_double((long long)scal[SC_LDOM]);
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < M; k += (int64_t)gridDim.x * blockDim.x) {
-        const SphCell g = sph_cell_of(keys[t.nstart[k]], t.ndepth[k], l);
+        const int d = t.ndepth[k];
+        const SphCell g = sph_cell_of(keys[t.nstart[k]], d > SPH_KEY_LEVELS ? klo[t.nstart[k]] : 0ull, d, l);
         out[16 * k + 1] = g.c[0]; out[16 * k + 2] = g.c[1]; out[16 * k + 3] = g.c[2];
     }
 }
@@ -133,7 +135,10 @@ int check_flags(sph_handle *h) {
                             "octree: two particles share all " + std::to_string(SPH_LEVELS) + " octant levels (coincident particles?); "
                             "the reference's build_octree! does not terminate on coincident input");
         if (f & ERRF_NODES) return sph_fail(h, SPH_ERR_TREE_NODES, "octree: node pool exhausted (set SPH_B200_NODE_FACTOR)");
-        if (f & ERRF_STACK) return sph_fail(h, SPH_ERR_CUDA, "tree walk stack overflow");
+        if (f & (ERRF_STACK | ERRF_STACK2)) return sph_fail(h, SPH_ERR_CUDA, "tree walk stack overflow");
+        if (f & ERRF_EXTRAS) return sph_fail(h, SPH_ERR_CUDA, "hydro: overflow list of the reverse-partner table exhausted");
+        if (f & ERRF_HALO)
+            return sph_fail(h, SPH_ERR_NCCL, "hydro: more cross-rank reverse pairs than the exchange buffer holds (set SPH_B200_HALO_CAP)");
         if (f & ERRF_NAN)
             return sph_fail(h, SPH_ERR_NAN, "time step is NaN (non-finite state); the reference's `while t < tEnd` loop ends here "
                                             "because minimum() propagates NaN (F/isothermal_sim.jl:158-166)");
@@ -208,6 +213,7 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
         SPH_CUDA(h, sph_launch_eos(h));
         TRACE("sph_launch_eos done");
     }
+    SPH_CUDA(h, sph_launch_extras_sort(h, t0, t1));
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_DENSITY + 1], st));
     // ---- force (second stream when overlapping) || walk (main stream)
     const bool ov = h->overlap && (!multi || h->nccl2 != nullptr);
@@ -388,7 +394,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(dalloc(&h->o_rho, N)); CK(dalloc(&h->o_h, N)); CK(dalloc(&h->o_phi, N)); CK(dalloc(&h->o_sumvdw, N));
     CK(dalloc(&h->o_mumax, N)); CK(dalloc(&h->o_cs, N)); CK(dalloc(&h->o_dkdt, N)); CK(dalloc(&h->o_ahyd, 3 * N));
     CK(dalloc(&h->o_g, 3 * N));
-    CK(dalloc(&h->keys, N)); CK(dalloc(&h->keys_alt, N)); CK(dalloc(&h->perm, N)); CK(dalloc(&h->perm_alt, N));
+    CK(dalloc(&h->keys, N)); CK(dalloc(&h->keys_alt, N)); CK(dalloc(&h->klo, N)); CK(dalloc(&h->perm, N)); CK(dalloc(&h->perm_alt, N));
     CK(dalloc(&h->pos4, NS)); CK(dalloc(&h->vel4, NS)); CK(dalloc(&h->hr, NS)); CK(dalloc(&h->pc, NS));
     CK(dalloc(&h->rho_s, NS)); CK(dalloc(&h->d2k, NS)); CK(dalloc(&h->kid, NS)); CK(dalloc(&h->nbr, NL * K));
     CK(dalloc(&h->ecnt, NL)); CK(dalloc(&h->ext, NL * (size_t)SPH_ECAP));
@@ -454,7 +460,7 @@ int sph_destroy(sph_handle *h) {
     if (h->nccl && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t)h->nccl);
     void *ptrs[] = {h->pos, h->vel, h->kent, h->acc, h->pos_half, h->vel_half, h->in_pos, h->in_vel, h->in_kent,
                     h->in_acc, h->o_rho, h->o_h, h->o_phi, h->o_sumvdw, h->o_mumax, h->o_cs, h->o_dkdt, h->o_ahyd,
-                    h->o_g, h->keys, h->keys_alt, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->pc,
+                    h->o_g, h->keys, h->keys_alt, h->klo, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->pc,
                     h->rho_s, h->d2k, h->kid, h->nbr, h->ecnt, h->ext, h->ovf, h->outbox, h->inbox, h->s_red, h->walk_buf, h->walk_part, h->cnt,
                     h->base, h->scal, h->stat_dev, h->red_partial, h->tree.nodeI, h->tree.nodeA, h->tree.nodeB,
                     h->tree.nodeC, h->tree.nodeD, h->tree.nodeW, h->tree.nodeBC, h->tree.parent, h->tree.arrive, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
@@ -704,7 +710,7 @@ int sph_get_octree(sph_handle *h, double *nodes, int64_t cap, int64_t *n_nodes) 
     if (int rc = ensure_scratch(h, (size_t)n * 16 * 8)) return rc;
     double *d = (double *)h->scratch;
     export_tree_kernel<<<148 * 4, 256, 0, h->stream>>>(h->tree, h->scal, h->p.m, n, d);
-    export_tree_centres_kernel<<<148 * 4, 256, 0, h->stream>>>(h->tree, h->scal, h->keys, n, d);
+    export_tree_centres_kernel<<<148 * 4, 256, 0, h->stream>>>(h->tree, h->scal, h->keys, h->klo, n, d);
     cudaError_t e = cudaMemcpyAsync(nodes, d, (size_t)n * 16 * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) return sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e));

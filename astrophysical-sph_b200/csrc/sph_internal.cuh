@@ -17,7 +17,8 @@
 
 #include "../../include/sph_b200.h"
 
-#define SPH_LEVELS 21           // octant levels held by one 63-bit key
+#define SPH_KEY_LEVELS 21       // octant levels held by one 63-bit key word
+#define SPH_LEVELS 42           // deepest cell: two key words (the second one only for particles that share the first)
 #define SPH_MAX_RANKS 16
 #define SPH_WALK_REC 2           // double4 per walk record of the octree (two nodes per 128-byte line)
 #define SPH_ECAP 64              // reverse partners per particle held in the extras table (more: overflow list)
@@ -32,32 +33,38 @@
 // :143-148): child_l = parent_l/2, child centre = parent centre -/+ child_l, octant bit = (x - c) > 0.
 // Only additions, subtractions and halvings: bit-identical to the Julia evaluation, so a particle
 // on a cell boundary lands in the same child as in the reference.
+// Word 0 holds levels 0..20, word 1 levels 21..41.  The sort uses word 0; word 1 is computed only for the (rare)
+// particles that share all of word 0 with a sorted neighbour and orders them inside that run (tree.cu), so trees
+// deeper than 21 levels - which build_octree! produces whenever two particles are closer than l / 2^21 per axis
+// (:213-227 subdivides until every leaf holds one particle) - are built like any other.
 // ---------------------------------------------------------------------------------------------
-HD uint64_t sph_octant_key(double x, double y, double z, double l) {
+HD uint64_t sph_octant_key_word(double x, double y, double z, double l, int word) {
     double cx = 0.0, cy = 0.0, cz = 0.0, L = l;
     uint64_t key = 0;
+    const int last = SPH_KEY_LEVELS * (word + 1);
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
-    for (int lev = 0; lev < SPH_LEVELS; ++lev) {
+    for (int lev = 0; lev < last; ++lev) {
         const double cl = L / 2;
         const unsigned ox = (x - cx) > 0, oy = (y - cy) > 0, oz = (z - cz) > 0;
-        key = (key << 3) | (uint64_t)((oz << 2) | (oy << 1) | ox);
+        key = (key << 3) | (uint64_t)((oz << 2) | (oy << 1) | ox);      // the bits of earlier words shift out
         cx = ox ? cx + cl : cx - cl;
         cy = oy ? cy + cl : cy - cl;
         cz = oz ? cz + cl : cz - cl;
         L = cl;
     }
-    return key;
+    return key & 0x7fffffffffffffffull;
 }
+HD uint64_t sph_octant_key(double x, double y, double z, double l) { return sph_octant_key_word(x, y, z, l, 0); }
 
-// Geometry of the depth-d cell on the path `key`: centre, bounds and half-width exactly as
+// Geometry of the depth-d cell on the path (khi, klo): centre, bounds and half-width exactly as
 // addNodes! produces them (F/gravOctree_Single.jl:110-140): for a parent (pc, pl): cl = pl/2,
 // lc = pc-cl, rc = pc+cl, mn = lc-cl, ctr = lc+cl, mx = rc+cl; low child = {lc,[mn,ctr]}, high = {rc,[ctr,mx]}.
 struct SphCell {
     double c[3], lo[3], hi[3], L;
 };
-HD SphCell sph_cell_of(uint64_t key, int depth, double l) {
+HD SphCell sph_cell_of(uint64_t khi, uint64_t klo, int depth, double l) {
     SphCell g;
     g.L = l;
     for (int a = 0; a < 3; ++a) { g.c[a] = 0.0; g.lo[a] = -l; g.hi[a] = l; }
@@ -66,7 +73,8 @@ HD SphCell sph_cell_of(uint64_t key, int depth, double l) {
 #endif
     for (int lev = 0; lev < depth; ++lev) {
         const double cl = g.L / 2;
-        const unsigned oct = (unsigned)(key >> (3 * (SPH_LEVELS - 1 - lev))) & 7u;
+        const unsigned oct = lev < SPH_KEY_LEVELS ? (unsigned)(khi >> (3 * (SPH_KEY_LEVELS - 1 - lev))) & 7u
+                                                  : (unsigned)(klo >> (3 * (2 * SPH_KEY_LEVELS - 1 - lev))) & 7u;
         for (int a = 0; a < 3; ++a) {
             const double lc = g.c[a] - cl, rc = g.c[a] + cl;
             const double mn = lc - cl, ctr = lc + cl, mx = rc + cl;
@@ -78,10 +86,10 @@ HD SphCell sph_cell_of(uint64_t key, int depth, double l) {
     return g;
 }
 
-// number of leading octant levels two keys share (21 = identical keys)
+// number of leading octant levels two key words share (21 = identical words)
 HD int sph_common_levels(uint64_t a, uint64_t b) {
     const uint64_t x = a ^ b;
-    if (x == 0) return SPH_LEVELS;
+    if (x == 0) return SPH_KEY_LEVELS;
 #ifdef __CUDA_ARCH__
     const int lz = __clzll((long long)x);
 #else
@@ -91,20 +99,21 @@ HD int sph_common_levels(uint64_t a, uint64_t b) {
 }
 
 #ifdef __CUDACC__
-// 1/sqrt(x) and 1/x from the hardware seed (MUFU.RSQ64H / RCP64H, ~2^-22 relative) plus one Newton step each:
-// relative error <= 1e-13, five FP64 instructions instead of the IEEE sequences with their slow-path calls.
+// 1/sqrt(x) and 1/x from the hardware seed (MUFU.RSQ64H / RCP64H read the high word of x: ~2^-21 relative) plus one
+// Newton step each: relative error <= 4e-13 - the parity bars are 1e-9 (hydro sums) and 1e-6 (gravity) - in five
+// and three instructions instead of the IEEE sequences with their slow-path calls.
 // x must be a normal positive number (squared distances / smoothing lengths of distinct particles are).
 __device__ __forceinline__ double fast_rsqrt(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x * y, y, 1.0);          // 1 - x y^2
-    return fma(y * e, 0.5 + 0.375 * e, y);         // y (1 + e/2 + 3 e^2/8)
+    const double e = fma(-(x * y), y, 1.0);        // 1 - x y^2
+    return fma(y * e, 0.5, y);                     // y (1 + e/2)
 }
 __device__ __forceinline__ double fast_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double e = fma(-x, y, 1.0);
-    return fma(y * e, 1.0 + e, y);                 // y (1 + e + e^2)
+    return fma(y, e, y);                           // y (1 + e)
 }
 
 // two ints in the bit pattern of a double (node records keep their integer fields next to the FP64 ones)
@@ -173,6 +182,7 @@ struct sph_handle {
            *o_cs = nullptr, *o_dkdt = nullptr, *o_ahyd = nullptr, *o_g = nullptr;
     // sort
     uint64_t *keys = nullptr, *keys_alt = nullptr;
+    uint64_t *klo = nullptr;    // second key word, valid for particles that share word 0 with a sorted neighbour
     int *perm = nullptr, *perm_alt = nullptr;
     void *sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
@@ -229,7 +239,7 @@ struct sph_handle {
 
 // scal[0..SC_RESET) is cleared at the start of every force evaluation; SC_STICKY accumulates error flags
 enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_KNN_RETRY, SC_OVF, SC_OUTBOX, SC_RESET = 15, SC_STICKY = 15, SC_COUNT = 16 };
-enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4, ERRF_NAN = 8, ERRF_EXTRAS = 16, ERRF_HALO = 32 };
+enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4, ERRF_NAN = 8, ERRF_EXTRAS = 16, ERRF_HALO = 32, ERRF_STACK2 = 64 };
 
 int sph_fail(sph_handle *h, int code, const std::string &msg);
 // cumulative count of kernel launches issued by the library in this process (bench.py's gpu_launches)
@@ -268,6 +278,7 @@ cudaError_t sph_launch_smoothing(sph_handle *h);                          // pos
 cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1, bool with_eos);   // rho (+ EOS) and extras of [t0, t1)
 cudaError_t sph_launch_outbox_header(sph_handle *h);
 cudaError_t sph_launch_extras_merge(sph_handle *h, int64_t t0, int64_t t1);
+cudaError_t sph_launch_extras_sort(sph_handle *h, int64_t t0, int64_t t1);     // fixed (ascending) order of every particle's extras
 cudaError_t sph_launch_eos(sph_handle *h);                                 // several ranks: hr, pc of ALL particles
 cudaError_t sph_launch_force(sph_handle *h, int64_t t0, int64_t t1);
 

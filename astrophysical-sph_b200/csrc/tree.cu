@@ -3,6 +3,8 @@
 // Replaces GJL.Octree / addNodes! / build_octree! / setCOMs! (F/gravOctree_Single.jl:78-227).
 // The reference builds the tree breadth-first by re-bucketing particle lists; here the tree is derived
 // from the sorted keys with one thread per particle / per node and no recursion:
+//   * particles are ordered by their octant path: sorted by key word 0 (levels 0..20), and the rare runs of particles
+//     that share all of word 0 are ordered by word 1 (levels 21..41) in place (key_runs_kernel);
 //   * particle i shares cpl(i-1), cpl(i) leading octant levels with its sorted neighbours;
 //   * the cells that START at particle i have depths cpl(i-1)+1 .. max(cpl(i-1),cpl(i))+1 (the last one
 //     is the leaf that holds i alone; the root is the depth-0 cell starting at particle 0);
@@ -65,13 +67,46 @@ __global__ void __launch_bounds__(TB) permute_kernel(const double *__restrict__ 
     }
 }
 
-// ---- tree: per-particle node counts ---------------------------------------------------------------
-__global__ void __launch_bounds__(TB) node_count_kernel(const uint64_t *__restrict__ keys, int64_t N,
-                                                         int *__restrict__ cnt, unsigned long long *__restrict__ scal) {
+// leading octant levels shared by sorted slots a and b (0..42); word 1 is only read (and only valid) when word 0 agrees
+__device__ __forceinline__ int common_levels2(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ klo, int64_t a, int64_t b) {
+    const int c = sph_common_levels(keys[a], keys[b]);
+    if (c < SPH_KEY_LEVELS) return c;
+    return SPH_KEY_LEVELS + sph_common_levels(klo[a], klo[b]);
+}
+
+// Runs of particles that share key word 0 (closer than l / 2^21 per axis): order each run by word 1, then by particle
+// id, in place (insertion sort by the thread of the run's first slot; the runs are a handful of particles).
+__global__ void __launch_bounds__(TB) key_runs_kernel(const double *__restrict__ pos, int64_t N, const uint64_t *__restrict__ keys,
+                                                       const unsigned long long *__restrict__ scal, int *__restrict__ perm,
+                                                       uint64_t *__restrict__ klo) {
+    const double l = __longlong_as_double((long long)scal[SC_LDOM]);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t k = keys[i];
-        const int a = i > 0 ? sph_common_levels(keys[i - 1], k) : -1;
-        const int b = i + 1 < N ? sph_common_levels(k, keys[i + 1]) : -1;
+        if (i > 0 && keys[i - 1] == k) continue;            // not the first slot of a run
+        if (i + 1 >= N || keys[i + 1] != k) continue;       // a run of one: word 1 is never consulted
+        int64_t e = i + 2;
+        while (e < N && keys[e] == k) ++e;
+        for (int64_t j = i; j < e; ++j) {
+            const int p = perm[j];
+            const uint64_t lo = sph_octant_key_word(pos[p], pos[p + N], pos[p + 2 * N], l, 1);
+            int64_t t = j;
+            while (t > i && (klo[t - 1] > lo || (klo[t - 1] == lo && perm[t - 1] > p))) {
+                klo[t] = klo[t - 1];
+                perm[t] = perm[t - 1];
+                --t;
+            }
+            klo[t] = lo;
+            perm[t] = p;
+        }
+    }
+}
+
+// ---- tree: per-particle node counts ---------------------------------------------------------------
+__global__ void __launch_bounds__(TB) node_count_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ klo, int64_t N,
+                                                         int *__restrict__ cnt, unsigned long long *__restrict__ scal) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = i > 0 ? common_levels2(keys, klo, i - 1, i) : -1;
+        const int b = i + 1 < N ? common_levels2(keys, klo, i, i + 1) : -1;
         if (a >= SPH_LEVELS || b >= SPH_LEVELS) atomicOr(&scal[SC_ERR], (unsigned long long)ERRF_DEPTH);
         const int mx = a > b ? a : b;
         cnt[i] = mx - a + 1;  // depths a+1 .. mx+1
@@ -79,7 +114,7 @@ __global__ void __launch_bounds__(TB) node_count_kernel(const uint64_t *__restri
 }
 
 // emits the (start, depth) node list in particle order; depth doubles as the 8-bit sort key
-__global__ void __launch_bounds__(TB) node_emit_kernel(const uint64_t *__restrict__ keys, int64_t N,
+__global__ void __launch_bounds__(TB) node_emit_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ klo, int64_t N,
                                                         const int *__restrict__ cnt, const int *__restrict__ base,
                                                         int64_t cap, int *__restrict__ old_start,
                                                         int *__restrict__ old_depth, uint64_t *__restrict__ dkey,
@@ -93,7 +128,7 @@ __global__ void __launch_bounds__(TB) node_emit_kernel(const uint64_t *__restric
     }
     if (bad) return;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-        const int a = i > 0 ? sph_common_levels(keys[i - 1], keys[i]) : -1;
+        const int a = i > 0 ? common_levels2(keys, klo, i - 1, i) : -1;
         const int n = cnt[i];
         const int o = base[i];
         for (int k = 0; k < n; ++k) {
@@ -132,7 +167,7 @@ __device__ __forceinline__ int lower_bound_key(const uint64_t *__restrict__ keys
 }
 
 // one thread per node (BFS id k): particle range, children, geometry, leaf payload
-__global__ void __launch_bounds__(TB) node_build_kernel(const uint64_t *__restrict__ keys, int64_t N,
+__global__ void __launch_bounds__(TB) node_build_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ klo, int64_t N,
                                                          const int *__restrict__ cnt, const int *__restrict__ base,
                                                          const int *__restrict__ bfs_old, const int *__restrict__ old_start,
                                                          const int *__restrict__ old_depth, const int *__restrict__ bfs_of_old,
@@ -148,18 +183,23 @@ __global__ void __launch_bounds__(TB) node_build_kernel(const uint64_t *__restri
         const int dleaf = (base[s + 1] - base[s]) + (d - (o - base[s])) - 1;  // deepest depth starting at s
         const bool leaf = d == dleaf;
         (void)cnt;
+        const uint64_t lo = d > SPH_KEY_LEVELS ? klo[s] : 0ull;   // word 1: cells below level 21 lie inside a run of equal word 0
         int e;  // end of the particle range
         if (d == 0) e = (int)N;
         else if (leaf) e = s + 1;
-        else {
-            const int sh = 3 * (SPH_LEVELS - d);
+        else if (d <= SPH_KEY_LEVELS) {
+            const int sh = 3 * (SPH_KEY_LEVELS - d);
             const uint64_t next_prefix = ((key >> sh) + 1ull) << sh;  // cannot overflow 64 bits: key < 2^63
             e = lower_bound_key(keys, s + 1, (int)N, next_prefix);
+        } else {
+            const int re = lower_bound_key(keys, s + 1, (int)N, key + 1ull);     // end of the run that shares word 0
+            const int sh = 3 * (2 * SPH_KEY_LEVELS - d);
+            e = lower_bound_key(klo, s + 1, re, ((lo >> sh) + 1ull) << sh);
         }
         t.nstart[k] = s;
         t.ncount[k] = e - s;
         t.ndepth[k] = d;
-        const SphCell g = sph_cell_of(key, d, l);
+        const SphCell g = sph_cell_of(key, lo, d, l);
         t.nodeB[k] = make_double4(g.lo[0], g.lo[1], g.lo[2], g.hi[0]);
         const double s2 = (g.L * 2) * (g.L * 2);  // s = node.Length*2 ; s^2  (F/gravOctree_Single.jl:257,265)
         t.nodeC[k] = make_double4(g.hi[1], g.hi[2], s2, g.L);
@@ -171,17 +211,21 @@ __global__ void __launch_bounds__(TB) node_build_kernel(const uint64_t *__restri
             t.nodeA[k] = make_double4(p.x, p.y, p.z, mass);  // leaf: rCOM = particle, Mass = m (:186-194, :69)
         } else {
             // non-empty octants of this cell = its children, contiguous in BFS order starting at the
-            // depth-(d+1) cell that starts at the same particle
-            const int sh = 3 * (SPH_LEVELS - 1 - d);
-            const uint64_t pre = (d == 0) ? 0ull : ((key >> (sh + 3)) << 3);
-            int nch = 0, lo = s, leafmask = 0;
-            for (int c = 1; c <= 8 && lo < e; ++c) {
-                const int nb = (c == 8) ? e : lower_bound_key(keys, lo, e, (pre + (uint64_t)c) << sh);
-                if (nb > lo) {
-                    if (nb - lo == 1) leafmask |= 1 << nch;   // child holds one particle = leaf
+            // depth-(d+1) cell that starts at the same particle; their digits are level d of the path
+            const bool w1 = d >= SPH_KEY_LEVELS;
+            const uint64_t *kw = w1 ? klo : keys;
+            const uint64_t kv = w1 ? klo[s] : key;
+            const int dl = w1 ? d - SPH_KEY_LEVELS : d;               // level inside the word
+            const int sh = 3 * (SPH_KEY_LEVELS - 1 - dl);
+            const uint64_t pre = (dl == 0) ? 0ull : ((kv >> (sh + 3)) << 3);
+            int nch = 0, lo_i = s, leafmask = 0;
+            for (int c = 1; c <= 8 && lo_i < e; ++c) {
+                const int nb = (c == 8) ? e : lower_bound_key(kw, lo_i, e, (pre + (uint64_t)c) << sh);
+                if (nb > lo_i) {
+                    if (nb - lo_i == 1) leafmask |= 1 << nch;   // child holds one particle = leaf
                     ++nch;
                 }
-                lo = nb;
+                lo_i = nb;
             }
             const int fc = bfs_of_old[o + 1];
             I = make_int2(fc, nch | (leafmask << 8));
@@ -249,8 +293,12 @@ cudaError_t sph_launch_domain_keys(sph_handle *h, const double *pos) {
     sph_note(2);
     absmax_kernel<<<grid_for(3 * h->N), TB, 0, st>>>(pos, 3 * h->N, h->scal);
     keys_kernel<<<grid_for(h->N), TB, 0, st>>>(pos, h->N, h->scal, h->keys_alt, h->perm_alt);
-    return sph_sort_pairs(h->keys_alt, h->perm_alt, h->keys, h->perm, h->N, nullptr, 0, 64, h->sort_tmp,
-                          h->sort_tmp_bytes, st);
+    cudaError_t e = sph_sort_pairs(h->keys_alt, h->perm_alt, h->keys, h->perm, h->N, nullptr, 0, 64, h->sort_tmp,
+                                   h->sort_tmp_bytes, st);
+    if (e != cudaSuccess) return e;
+    sph_note(1);
+    key_runs_kernel<<<grid_for(h->N), TB, 0, st>>>(pos, h->N, h->keys, h->scal, h->perm, h->klo);
+    return cudaGetLastError();
 }
 
 cudaError_t sph_launch_permute(sph_handle *h, const double *pos, const double *vel, const double *kent) {
@@ -264,10 +312,10 @@ cudaError_t sph_launch_tree(sph_handle *h) {
     SphTree &t = h->tree;
     const int64_t N = h->N;
     sph_note(6);
-    node_count_kernel<<<grid_for(N), TB, 0, st>>>(h->keys, N, h->cnt, h->scal);
+    node_count_kernel<<<grid_for(N), TB, 0, st>>>(h->keys, h->klo, N, h->cnt, h->scal);
     cudaError_t e = sph_exclusive_scan(h->cnt, h->base, N, h->sort_tmp, h->sort_tmp_bytes, st);
     if (e != cudaSuccess) return e;
-    node_emit_kernel<<<grid_for(N), TB, 0, st>>>(h->keys, N, h->cnt, h->base, t.cap, t.old_start, t.old_depth,
+    node_emit_kernel<<<grid_for(N), TB, 0, st>>>(h->keys, h->klo, N, h->cnt, h->base, t.cap, t.old_start, t.old_depth,
                                                   t.dkey_in, t.dval_in, h->scal);
     level_init_kernel<<<1, TB, 0, st>>>(t.level_start, h->scal);
     // stable counting sort by depth (one 8-bit pass) = breadth-first node order of build_octree!
@@ -275,7 +323,7 @@ cudaError_t sph_launch_tree(sph_handle *h) {
                        h->sort_tmp, h->sort_tmp_bytes, st);
     if (e != cudaSuccess) return e;
     node_inverse_kernel<<<grid_for(t.cap), TB, 0, st>>>(t.dval_out, t.old_depth, h->scal, t.bfs_of_old, t.level_start);
-    node_build_kernel<<<grid_for(t.cap), TB, 0, st>>>(h->keys, N, h->cnt, h->base, t.dval_out, t.old_start,
+    node_build_kernel<<<grid_for(t.cap), TB, 0, st>>>(h->keys, h->klo, N, h->cnt, h->base, t.dval_out, t.old_start,
                                                        t.old_depth, t.bfs_of_old, h->pos4, h->p.m, h->scal, t);
     cudaMemsetAsync(t.arrive, 0, sizeof(int) * (size_t)t.cap, st);
     com_bottomup_kernel<<<grid_for(t.cap), TB, 0, st>>>(t, h->scal);

@@ -37,8 +37,9 @@ enum sph_status {
     SPH_ERR_INVALID = -1,     /* bad argument (null pointer, K > N, N < 64, ...)                              */
     SPH_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed; message holds cudaGetErrorString        */
     SPH_ERR_NO_DEVICE = -3,   /* no sm_100 device visible: the library never falls back to the CPU             */
-    SPH_ERR_TREE_DEPTH = -4,  /* two particles share all 21 octant levels (coincident or closer than l/2^21);
-                                 the reference loops forever here (F/gravOctree_Single.jl:217-223)              */
+    SPH_ERR_TREE_DEPTH = -4,  /* two particles share all 42 octant levels (coincident, or closer than l/2^42 per
+                                 axis); the reference loops forever on coincident particles
+                                 (F/gravOctree_Single.jl:217-223)                                               */
     SPH_ERR_TREE_NODES = -5,  /* node pool (3 N + 1024 nodes; SPH_B200_NODE_FACTOR enlarges it) exhausted         */
     SPH_ERR_NCCL = -6,        /* NCCL call failed                                                              */
     SPH_ERR_STATE = -7,       /* call sequence error (e.g. sph_step before sph_upload)                         */

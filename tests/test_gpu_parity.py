@@ -254,6 +254,26 @@ def test_minimum_size_and_lattice_ties(sph, oracle):
     check_against_oracle(sph, oracle, "isothermal", pos, np.asfortranarray(np.zeros_like(pos)), None, c, args, Kh=20)
 
 
+def test_deep_tree_two_scales(sph, oracle):
+    """Two length scales 1e-8 apart: a Gaussian sphere with a tight clump (sigma = 1e-8) and pairs down to 1e-11 of
+    the domain.  build_octree! subdivides until every leaf holds one particle at ANY depth
+    (F/gravOctree_Single.jl:213-227); the one-word octant key resolves 21 levels, the second key word 42: the tree must
+    equal the oracle's unbounded BFS node for node, and every result must hold its usual tolerance."""
+    rng = np.random.default_rng(21)
+    base = rng.standard_normal((4000, 3))
+    clump = base[100] + 1e-8 * rng.standard_normal((80, 3))
+    pairs = np.concatenate([base[200 + k] + s * rng.standard_normal(3)[None, :] for k, s in enumerate((1e-7, 1e-9, 1e-10, 1e-11, 3e-11))])
+    pos = np.asfortranarray(np.concatenate([base, clump, pairs]))
+    pos = np.asfortranarray(pos[rng.permutation(pos.shape[0])])
+    N = pos.shape[0]
+    vel = np.asfortranarray(0.1 * rng.standard_normal(pos.shape))
+    c = dict(m=1.0 / N, cs=1.0, G=1.0, theta=0.576, alpha=1.0, beta=2.0, Kh=50)
+    args = dict(m=c["m"], cs=1.0, G=1.0, theta=0.576, alpha=1.0, beta=2.0)
+    st = check_against_oracle(sph, oracle, "isothermal", pos, vel, None, c, args)
+    assert st[1] > 30, st          # deeper than one key word resolves
+    check_hinted_search(sph, oracle, "isothermal", pos, vel, None, c, args, max_retry_frac=0.2)
+
+
 def test_coincident_particles_are_reported(sph):
     """The reference never returns on coincident particles (Appendix B-7); the library reports it."""
     rng = np.random.default_rng(4)
@@ -461,12 +481,13 @@ def test_run_simulation_writes_reference_files(sph, oracle, tmp_path):
 
 @pytest.mark.parametrize("env", ["SPH_B200_WALK_DFS=1", "SPH_B200_WALK_T=1", "SPH_B200_WALK_ROWS=1", "SPH_B200_NO_OVERLAP=1",
                                  "SPH_B200_KNN_SORT=1", "SPH_B200_NO_HINT=1", "SPH_B200_SPH_TILE=1", "SPH_B200_SPH_TILE=0",
-                                 "SPH_B200_ECAP=8"])
+                                 "SPH_B200_ECAP=8", "SPH_B200_WALK_FORCE_DEEP=1"])
 def test_alternative_paths_agree(sph, env):
     """Every switchable kernel variant (shared walk without the pair queue, pair queue for single-lane cells only, one
     block row per tile, serial force / walk, sorted instead of selected hits, unhinted search, shared-memory tile /
-    direct-gather SPH sums, an 8-entry extras table that sends reverse partners through the overflow list) passes the
-    same two-step parity check against the oracle."""
+    direct-gather SPH sums, an 8-entry extras table that sends reverse partners through the overflow list, the
+    42-level walk variant that takes over when the regular walk's stack overflows) passes the same two-step parity
+    check against the oracle."""
     import subprocess
     import sys
 
