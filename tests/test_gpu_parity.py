@@ -108,8 +108,10 @@ def check_against_oracle(sph, O, eos, pos, vel, K, c, args, Kh=None, nthreads=No
     # ---- hydro force, per particle, with the cancellation guard S_i = sum_j ||term_ij||
     assert_hydro_force(hy["ahyd"], oh, hydro_term_scale(pos, vel, oh, dict(c, Kh=Kh), eos, K))
     # sum_j v_ij.gradW_ij is pure cancellation for e.g. solid-body rotation: compare against the summed term sizes
+    # (a particle whose neighbours ALL sit at the kernel edge, q = 2 - 1e-7, has terms ~ (2 - q)^2 that are 1e-14 of
+    # the typical ones and lose digits in 2 - q itself: the scale is floored at 1e-6 of the median particle's)
     S = vdw_scale(pos, vel, oh["idx"], oh["r"], oh["h"], eos == "polytropic")
-    assert (np.abs(hy["sum_vdw"] - oh["sum_vdw"]) <= TOL_SPH * S + 1e-300).all()
+    assert (np.abs(hy["sum_vdw"] - oh["sum_vdw"]) <= TOL_SPH * np.maximum(S, 1e-6 * np.median(S)) + 1e-300).all()
     assert np.array_equal(hy["mumax"], oh["mumax"])
     if eos == "polytropic":
         assert np.abs(hy["cs_i"] / oh["cs_i"] - 1).max() < TOL_SPH
