@@ -123,17 +123,17 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // TILE: the block's K x 128 list tile and the records of the key-order window [tile - TW, tile + 128 + TW) are staged
 // in shared memory by bulk async copies; neighbours outside the window are gathered from global memory.
 // ---------------------------------------------------------------------------------------------------
-constexpr int TW = 96;                  // window margin on each side of the 128-target tile
+constexpr int TW = 128;                 // window margin on each side of the 128-target tile
 constexpr int TWIN = HB + 2 * TW;       // records in the window
 
 // EOS closure of one particle: isothermal P = cs^2 rho (F/isothermal_hydroKDTree.jl:190), c = cs; polytropic
 // P = K rho^gamma (F/polytrope_hydroKDTree.jl:216), c_i = sqrt(gamma K rho^(gamma-1)) (:186).
-// hr = {h, rho}; prec = the 128-byte record the force pass gathers per neighbour: {x, y, z, d2k | vx, vy, vz, K |
-// rho, P/rho^2, h, c | unused}.  One record = one cache line: a gather of three separate 32-byte arrays costs three L1
-// tag look-ups per lane, and the force kernel is bound by exactly those.
-__device__ __forceinline__ void eos_store(int64_t s, const double4 &pi, const double4 &vi, double h, double rho, int poly,
-                                          double cs, double gamma, double2 *__restrict__ hr, double4 *__restrict__ prec) {
-    const double Kent = vi.w;
+// hr = {h, rho}; pc = {rho, P/rho^2, h, c}: the 32-byte record the force pass gathers per neighbour next to pos4 and vel4.
+// (Measured and dropped: ONE 128-byte record {pos | vel | pc | pad} per particle, i.e. one cache line per gathered
+// neighbour instead of three sectors in three lines - force 0.73 -> 1.08 ms at N = 1e6: a line of a 32-byte array holds
+// four key-adjacent particles, which are mostly neighbours too, so the three arrays use L1 far better.)
+__device__ __forceinline__ void eos_store(int64_t s, double h, double rho, double Kent, int poly, double cs, double gamma,
+                                          double2 *__restrict__ hr, double4 *__restrict__ pc) {
     double P, c;
     if (!poly) {
         P = cs * cs * rho;
@@ -143,9 +143,7 @@ __device__ __forceinline__ void eos_store(int64_t s, const double4 &pi, const do
         P = Kent * pow(rho, gamma);
     }
     hr[s] = make_double2(h, rho);
-    prec[4 * s] = pi;
-    prec[4 * s + 1] = vi;
-    prec[4 * s + 2] = make_double4(rho, P / (rho * rho), h, c);
+    pc[s] = make_double4(rho, P / (rho * rho), h, c);
 }
 
 // EOS: with one rank the density pass closes the EOS of its target on the spot (every particle is a target);
@@ -157,7 +155,7 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int 
                                                       double m, int poly, unsigned long long *__restrict__ scal,
                                                       ExtrasOut x, double *__restrict__ rho_out,
                                                       const double4 *__restrict__ vel4, double cs, double gamma,
-                                                      double2 *__restrict__ hr, double4 *__restrict__ prec) {
+                                                      double2 *__restrict__ hr, double4 *__restrict__ pc) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     if (scal[SC_ERR] != 0ull) return;
     const int64_t s0 = t0 + (int64_t)blockIdx.x * HB;
@@ -226,7 +224,7 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int 
         defer &= defer - 1ull;
         push_extra(x, lst[j * lstride], (int)s, scal);
     }
-    if (EOS) eos_store(s, pi, vel4[s], h, m * sum, poly, cs, gamma, hr, prec);
+    if (EOS) eos_store(s, h, m * sum, poly ? vel4[s].w : 0.0, poly, cs, gamma, hr, pc);
     else rho_out[s] = m * sum;
 }
 
@@ -291,13 +289,12 @@ __global__ void __launch_bounds__(HB) extras_sort_kernel(int64_t NL, int64_t t0,
 __global__ void __launch_bounds__(HB) eos_kernel(int64_t N, const double *__restrict__ rho_s, const double4 *__restrict__ pos4,
                                                   const double4 *__restrict__ vel4, int poly, double cs, double gamma,
                                                   const unsigned long long *__restrict__ scal, double2 *__restrict__ hr,
-                                                  double4 *__restrict__ prec) {
+                                                  double4 *__restrict__ pc) {
     if (scal[SC_ERR] != 0ull) return;
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
-    const double4 pi = pos4[s];
-    const double h = sqrt(pi.w) / 2;                 // h = r[:, end] ./ 2   (:151)
-    eos_store(s, pi, vel4[s], h, rho_s[s], poly, cs, gamma, hr, prec);
+    const double h = sqrt(pos4[s].w) / 2;            // h = r[:, end] ./ 2   (:151)
+    eos_store(s, h, rho_s[s], poly ? vel4[s].w : 0.0, poly, cs, gamma, hr, pc);
 }
 
 // pos4.w = d2k for ALL particles (after the d2k all-gather in multi-GPU runs): the density and force passes read the
@@ -368,7 +365,8 @@ __device__ __forceinline__ void pair_terms(const Target &t, const double4 &pj, c
 
 template <bool POLY, bool TILE>
 __global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int64_t NL, int64_t NS, int K, int64_t t0, int64_t t1,
-                                                    const double4 *__restrict__ prec, const int *__restrict__ nbr,
+                                                    const double4 *__restrict__ pos4, const double4 *__restrict__ vel4,
+                                                    const double4 *__restrict__ pc, const int *__restrict__ nbr,
                                                     const int *__restrict__ perm, const int *__restrict__ kid,
                                                     const int *__restrict__ ecnt, const int *__restrict__ ext, int ecap,
                                                     double m, double alpha, double beta,
@@ -381,13 +379,14 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int6
     const int64_t s = s0 + threadIdx.x;
     const int *lst = nbr + s;
     int64_t lstride = NL;
-    const double4 *wrec = nullptr;
+    const double4 *wpos = nullptr, *wvel = nullptr, *wpc = nullptr;
     int64_t w0 = 0;
     int wn = 0;
     if (TILE) {
         unsigned long long *bar = reinterpret_cast<unsigned long long *>(dyn_smem);
-        double4 *s_rec = reinterpret_cast<double4 *>(dyn_smem + 128);
-        int *s_idx = reinterpret_cast<int *>(s_rec + 4 * TWIN);
+        double4 *s_pos = reinterpret_cast<double4 *>(dyn_smem + 128);
+        double4 *s_vel = s_pos + TWIN, *s_pc = s_vel + TWIN;
+        int *s_idx = reinterpret_cast<int *>(s_pc + TWIN);
         w0 = s0 - TW < 0 ? 0 : s0 - TW;
         const int64_t w1 = s0 + HB + TW > N ? N : s0 + HB + TW;
         wn = (int)(w1 - w0);
@@ -397,21 +396,24 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int6
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const unsigned wb = (unsigned)(wn * 4 * sizeof(double4));
-            mbar_expect_tx(bar, wb + (unsigned)((size_t)K * HB * sizeof(int)));
-            bulk_g2s(s_rec, prec + 4 * w0, wb, bar);
+            const unsigned wb = (unsigned)(wn * sizeof(double4));
+            mbar_expect_tx(bar, 3 * wb + (unsigned)((size_t)K * HB * sizeof(int)));
+            bulk_g2s(s_pos, pos4 + w0, wb, bar);
+            bulk_g2s(s_vel, vel4 + w0, wb, bar);
+            bulk_g2s(s_pc, pc + w0, wb, bar);
             for (int j = 0; j < K; ++j) bulk_g2s(s_idx + j * HB, nbr + (int64_t)j * NL + s0, HB * sizeof(int), bar);
         }
         mbar_wait(bar, 0);
         lst = s_idx + threadIdx.x;
         lstride = HB;
-        wrec = s_rec;
+        wpos = s_pos; wvel = s_vel; wpc = s_pc;
     }
     if (s >= t1) return;
     Target t;
     {
-        const double4 *own = TILE ? wrec + 4 * (s - w0) : prec + 4 * s;
-        const double4 pi = own[0], vi = own[1], ci = own[2];
+        const double4 pi = TILE ? wpos[s - w0] : pos4[s];
+        const double4 vi = TILE ? wvel[s - w0] : vel4[s];
+        const double4 ci = TILE ? wpc[s - w0] : pc[s];
         t.x = pi.x; t.y = pi.y; t.z = pi.z; t.h = ci.z;
         t.vx = vi.x; t.vy = vi.y; t.vz = vi.z;
         t.rho = ci.x; t.prr = ci.y; t.cs = ci.w;
@@ -426,12 +428,17 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int6
     for (int j = 0; j < K; ++j) {
         const int nj = lst[j * lstride];
         if (nj == (int)s) continue;      // lists arrive unordered from the grouped search: self is recognised by index
-        const double4 *rj = prec + 4 * (int64_t)nj;
+        double4 pj, vj, cj;
         if (TILE) {
             const unsigned loc = (unsigned)(nj - (int)w0);
-            if (loc < (unsigned)wn) rj = wrec + 4 * loc;          // generic loads: window or global
+            const bool in = loc < (unsigned)wn;
+            const double4 *pp = in ? wpos + loc : pos4 + nj;
+            const double4 *vp = in ? wvel + loc : vel4 + nj;
+            const double4 *cp = in ? wpc + loc : pc + nj;
+            pj = *pp; vj = *vp; cj = *cp;
+        } else {
+            pj = pos4[nj]; vj = vel4[nj]; cj = pc[nj];
         }
-        const double4 pj = rj[0], vj = rj[1], cj = rj[2];
         // does nj's list contain s?  then its reaction on s is gathered here (mutual pair)
         const double d2 = sph_d2_exact(t.x - pj.x, t.y - pj.y, t.z - pj.z);
         const bool rev = in_list_of(d2, pj.w, (int)s, nj, perm, kid);
@@ -443,8 +450,7 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int6
     double dummy_s = 0.0, dummy_m = 0.0;
     for (int e = 0; e < ne; ++e) {
         const int k = ext[(int64_t)e * NL + s];
-        const double4 *rj = prec + 4 * (int64_t)k;
-        const double4 pj = rj[0], vj = rj[1], cj = rj[2];
+        const double4 pj = pos4[k], vj = vel4[k], cj = pc[k];
         pair_terms<POLY, false>(t, pj, vj, cj, true, m, alpha, beta, ax, ay, az, dk, dummy_s, dummy_m);
     }
     ahyd[s] = ax; ahyd[s + NS] = ay; ahyd[s + 2 * NS] = az;
@@ -457,7 +463,8 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int6
 // Each such particle scans the list for its entries and adds them in ascending index order (rare, deterministic).
 template <bool POLY>
 __global__ void __launch_bounds__(HB) force_overflow_kernel(int64_t NS, int64_t t0, int64_t t1,
-                                                             const double4 *__restrict__ prec, const int *__restrict__ ecnt,
+                                                             const double4 *__restrict__ pos4, const double4 *__restrict__ vel4,
+                                                             const double4 *__restrict__ pc, const int *__restrict__ ecnt,
                                                              int ecap, const int2 *__restrict__ ovf, int ovcap, double m,
                                                              double alpha, double beta, const unsigned long long *__restrict__ scal,
                                                              double *__restrict__ ahyd, double *__restrict__ dkdt) {
@@ -469,7 +476,7 @@ __global__ void __launch_bounds__(HB) force_overflow_kernel(int64_t NS, int64_t 
     if (s >= t1 || ecnt[s] <= ecap) return;
     Target t;
     {
-        const double4 pi = prec[4 * s], vi = prec[4 * s + 1], ci = prec[4 * s + 2];
+        const double4 pi = pos4[s], vi = vel4[s], ci = pc[s];
         t.x = pi.x; t.y = pi.y; t.z = pi.z; t.h = ci.z;
         t.vx = vi.x; t.vy = vi.y; t.vz = vi.z;
         t.rho = ci.x; t.prr = ci.y; t.cs = ci.w;
@@ -484,8 +491,7 @@ __global__ void __launch_bounds__(HB) force_overflow_kernel(int64_t NS, int64_t 
             if (p.x == (int)s && p.y > last && p.y < best) best = p.y;
         }
         if (best == 0x7fffffff) break;
-        const double4 *rj = prec + 4 * (int64_t)best;
-        const double4 pj = rj[0], vj = rj[1], cj = rj[2];
+        const double4 pj = pos4[best], vj = vel4[best], cj = pc[best];
         pair_terms<POLY, false>(t, pj, vj, cj, true, m, alpha, beta, ax, ay, az, dk, d0, d1);
         last = best;
     }
@@ -502,7 +508,7 @@ inline ExtrasOut extras_of(sph_handle *h, int64_t t0, int64_t t1) {
 }
 
 constexpr size_t DENS_SMEM = 128 + sizeof(double4) * TWIN;          // + K * HB * 4
-constexpr size_t FORCE_SMEM = 128 + 4 * sizeof(double4) * TWIN;     // + K * HB * 4
+constexpr size_t FORCE_SMEM = 128 + 3 * sizeof(double4) * TWIN;     // + K * HB * 4
 
 }  // namespace
 
@@ -538,16 +544,16 @@ static cudaError_t launch_density(sph_handle *h, int64_t t0, int64_t t1) {
         }
         density_kernel<true, EOS><<<blocks, HB, smem, h->stream>>>(h->N, h->NL, h->K, t0, t1, h->pos4, h->nbr, h->perm, h->kid,
                                                                    h->p.m, poly, h->scal, x, h->rho_s, h->vel4, h->p.cs, h->p.gamma,
-                                                                   h->hr, h->prec);
+                                                                   h->hr, h->pc);
     } else {
         density_kernel<false, EOS><<<blocks, HB, 0, h->stream>>>(h->N, h->NL, h->K, t0, t1, h->pos4, h->nbr, h->perm, h->kid,
                                                                  h->p.m, poly, h->scal, x, h->rho_s, h->vel4, h->p.cs, h->p.gamma,
-                                                                 h->hr, h->prec);
+                                                                 h->hr, h->pc);
     }
     return cudaGetLastError();
 }
 
-// with_eos: one rank - the EOS of every target is closed in the same kernel (hr, prec written); several ranks - only
+// with_eos: one rank - the EOS of every target is closed in the same kernel (hr, pc written); several ranks - only
 // rho_s of the owned targets, sph_launch_eos follows the all-gather
 cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1, bool with_eos) {
     if (t1 <= t0) return cudaSuccess;
@@ -577,7 +583,7 @@ cudaError_t sph_launch_extras_sort(sph_handle *h, int64_t t0, int64_t t1) {
 cudaError_t sph_launch_eos(sph_handle *h) {
     sph_note(1);
     eos_kernel<<<(int)((h->N + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->rho_s, h->pos4, h->vel4, h->p.eos == SPH_EOS_POLYTROPIC,
-                                                                  h->p.cs, h->p.gamma, h->scal, h->hr, h->prec);
+                                                                  h->p.cs, h->p.gamma, h->scal, h->hr, h->pc);
     return cudaGetLastError();
 }
 
@@ -593,15 +599,15 @@ static cudaError_t launch_force(sph_handle *h, int64_t t0, int64_t t1) {
             if (e != cudaSuccess) return e;
             attr = true;
         }
-        force_kernel<POLY, true><<<blocks, HB, smem, h->stream>>>(h->N, h->NL, h->NS, h->K, t0, t1, h->prec, h->nbr,
+        force_kernel<POLY, true><<<blocks, HB, smem, h->stream>>>(h->N, h->NL, h->NS, h->K, t0, t1, h->pos4, h->vel4, h->pc, h->nbr,
                                                                   h->perm, h->kid, h->ecnt, h->ext, h->ecap, h->p.m, h->p.alpha,
                                                                   h->p.beta, h->scal, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax);
     } else {
-        force_kernel<POLY, false><<<blocks, HB, 0, h->stream>>>(h->N, h->NL, h->NS, h->K, t0, t1, h->prec, h->nbr,
+        force_kernel<POLY, false><<<blocks, HB, 0, h->stream>>>(h->N, h->NL, h->NS, h->K, t0, t1, h->pos4, h->vel4, h->pc, h->nbr,
                                                                 h->perm, h->kid, h->ecnt, h->ext, h->ecap, h->p.m, h->p.alpha,
                                                                 h->p.beta, h->scal, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax);
     }
-    force_overflow_kernel<POLY><<<blocks, HB, 0, h->stream>>>(h->NS, t0, t1, h->prec, h->ecnt, h->ecap, h->ovf,
+    force_overflow_kernel<POLY><<<blocks, HB, 0, h->stream>>>(h->NS, t0, t1, h->pos4, h->vel4, h->pc, h->ecnt, h->ecap, h->ovf,
                                                               (int)h->ovcap, h->p.m, h->p.alpha, h->p.beta, h->scal, h->s_ahyd,
                                                               h->s_dkdt);
     return cudaGetLastError();
