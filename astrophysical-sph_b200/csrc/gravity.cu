@@ -33,7 +33,12 @@ __constant__ double c_gk[13] = {4.0 / 3, 6.0 / 5, 1.0 / 2, 2.0 / 3, 3.0 / 10, 1.
 
 // Kernels (F/gravOctree_Single.jl:5-29): grad(PHI)/r and PHI of the spline-softened potential, written in
 // q = r/h and 1/h (same polynomials; one reciprocal and one rsqrt instead of seven divisions)
-__device__ __forceinline__ void grav_pair(double d_sq, double h, double &gPHI, double &PHI) {
+#ifdef WALK_NOINLINE_NEAR
+#define NEAR_INLINE __noinline__
+#else
+#define NEAR_INLINE __forceinline__
+#endif
+__device__ NEAR_INLINE void grav_pair(double d_sq, double h, double &gPHI, double &PHI) {
     const double rinv = d_sq > 0.0 ? fast_rsqrt(d_sq) : 0.0;
     const double r = d_sq * rinv;
     const double hinv = fast_rcp(h);
@@ -273,6 +278,24 @@ struct GpWarp {
     int q[GP_SOFT + SLACK];              // pairs: node | target lane << 27
 };
 
+// build-time experiments (tools/build_variants.sh): resident blocks of the pair walk, rare paths out of line
+#ifndef WALK_MINB
+#define WALK_MINB 8
+#endif
+#ifdef WALK_NOINLINE_C2
+#define C2_INLINE __noinline__
+#else
+#define C2_INLINE __forceinline__
+#endif
+
+// clause 2 of the acceptance rule evaluated with the reference's expression: h_i^2 / mindist^2(p_i, cell) < 0.25
+__device__ C2_INLINE bool clause2_exact(const double4 *__restrict__ nodeBC, int n, double px, double py, double pz, double hi2) {
+    const double4 B = nodeBC[2 * (int64_t)n];
+    const double4 C = nodeBC[2 * (int64_t)n + 1];
+    const double ex = axis_dist_bits(B.x, B.w, px), ey = axis_dist_bits(B.y, C.x, py), ez = axis_dist_bits(B.z, C.y, pz);
+    return quotient_less(hi2, sph_d2_exact(ex, ey, ez), 0.25);
+}
+
 // the reference's acceptance rule (:265) for one particle and one internal cell: same arithmetic as walk_kernel
 __device__ __forceinline__ bool cell_accepted(const SphTree &t, int n, double s_sq, double radius, double d_sq,
                                               double px, double py, double pz, double hi2, double h2x,
@@ -288,12 +311,7 @@ __device__ __forceinline__ bool cell_accepted(const SphTree &t, int n, double s_
     // clause 2: h_i*h_i / mind2 < 0.25, proven from d > radius + 2 h_i, else the reference's expression
     if (accept) {
         const double w = radius + h2x;
-        if (!(d_sq > w * w)) {
-            const double4 B = t.nodeBC[2 * (int64_t)n];
-            const double4 C = t.nodeBC[2 * (int64_t)n + 1];
-            const double ex = axis_dist_bits(B.x, B.w, px), ey = axis_dist_bits(B.y, C.x, py), ez = axis_dist_bits(B.z, C.y, pz);
-            accept = quotient_less(hi2, sph_d2_exact(ex, ey, ez), 0.25);
-        }
+        if (!(d_sq > w * w)) accept = clause2_exact(t.nodeBC, n, px, py, pz, hi2);
     }
     return accept;
 }
@@ -311,7 +329,7 @@ __device__ __forceinline__ void leaf_pair(double d_sq, double hi, double hj, dou
 }
 
 template <bool COUNT, bool DEEP>
-__global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : 8) walk_pairs_kernel(int64_t N, int nranks, int rank, int64_t chunk,
+__global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : WALK_MINB) walk_pairs_kernel(int64_t N, int nranks, int rank, int64_t chunk,
                                                                        const double4 *__restrict__ pos4,
                                                                        const double2 *__restrict__ hr, SphTree t,
                                                                        double theta_sq, double th_lo, double th_hi, double m,

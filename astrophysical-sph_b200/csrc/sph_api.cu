@@ -424,7 +424,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
         const size_t C = (size_t)t.cap;
         CK(dalloc(&t.nodeI, C)); CK(dalloc(&t.nodeA, C)); CK(dalloc(&t.nodeB, C)); CK(dalloc(&t.nodeC, C)); CK(dalloc(&t.nodeD, C)); CK(dalloc(&t.nodeW, SPH_WALK_REC * C)); CK(dalloc(&t.nodeBC, 2 * C));
         CK(dalloc(&t.nstart, C)); CK(dalloc(&t.ncount, C)); CK(dalloc(&t.ndepth, C));
-        CK(dalloc(&t.parent, C)); CK(dalloc(&t.arrive, C));
+        CK(dalloc(&t.parent, C)); CK(dalloc(&t.arrive, C)); CK(dalloc(&t.leaf_of, (size_t)h->N));
         CK(dalloc(&t.old_start, C)); CK(dalloc(&t.old_depth, C));
         CK(dalloc(&t.dkey_in, C)); CK(dalloc(&t.dkey_out, C)); CK(dalloc(&t.dval_in, C)); CK(dalloc(&t.dval_out, C));
         CK(dalloc(&t.bfs_of_old, C)); CK(dalloc(&t.level_start, (size_t)SPH_LEVELS + 8));
@@ -463,7 +463,7 @@ int sph_destroy(sph_handle *h) {
                     h->o_g, h->keys, h->keys_alt, h->klo, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->pc,
                     h->rho_s, h->d2k, h->kid, h->nbr, h->ecnt, h->ext, h->ovf, h->outbox, h->inbox, h->s_red, h->walk_buf, h->walk_part, h->cnt,
                     h->base, h->scal, h->stat_dev, h->red_partial, h->tree.nodeI, h->tree.nodeA, h->tree.nodeB,
-                    h->tree.nodeC, h->tree.nodeD, h->tree.nodeW, h->tree.nodeBC, h->tree.parent, h->tree.arrive, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
+                    h->tree.nodeC, h->tree.nodeD, h->tree.nodeW, h->tree.nodeBC, h->tree.parent, h->tree.arrive, h->tree.leaf_of, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
                     h->tree.old_depth, h->tree.dkey_in, h->tree.dkey_out, h->tree.dval_in, h->tree.dval_out,
                     h->tree.bfs_of_old, h->tree.level_start};
     for (void *p : ptrs)

@@ -146,6 +146,7 @@ struct SphTree {
     double2 *nodeD = nullptr;  // internal nodes: {(2 Length)^2, upper bound of the distance from rCOM to any point of the cell}
     int *nstart = nullptr, *ncount = nullptr, *ndepth = nullptr;
     int *parent = nullptr, *arrive = nullptr;   // bottom-up COM sweep: parent id, number of finished children
+    int *leaf_of = nullptr;                      // leaf node of every sorted slot
     // build scratch
     int *old_start = nullptr, *old_depth = nullptr;  // node list in (start, depth) order
     uint64_t *dkey_in = nullptr, *dkey_out = nullptr;

@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(TB) node_build_kernel(const uint64_t *__restri
         if (leaf) {
             I = make_int2(s, 0);
             t.nodeI[k] = I;
+            t.leaf_of[s] = (int)k;
             const double4 p = pos4[s];
             t.nodeA[k] = make_double4(p.x, p.y, p.z, mass);  // leaf: rCOM = particle, Mass = m (:186-194, :69)
         } else {

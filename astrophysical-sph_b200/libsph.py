@@ -16,7 +16,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsph_b200.so")
+# SPH_B200_LIB selects another build of the same sources (tuning variants, csrc/Makefile VARIANT=...)
+LIB_PATH = os.environ.get("SPH_B200_LIB") or os.path.join(_HERE, "libsph_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 ISOTHERMAL, POLYTROPIC = 0, 1

@@ -386,7 +386,8 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: N fixed (the metric's definition); weak: N = n x world (n per GPU, default config N / 8)")
-    ap.add_argument("--n", type=int, default=0, help="override the particle count (per GPU with --scaling weak)")
+    ap.add_argument("--particles", "--n", dest="n", type=int, default=0,
+                    help="override the particle count (per GPU with --scaling weak)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -400,7 +401,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"), __file__,
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--config", args.config,
-               "--scaling", args.scaling, "--n", str(args.n)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+               "--scaling", args.scaling, "--particles", str(args.n)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
         sys.exit(subprocess.call(cmd))
     run_b200(args, rank, world, local_rank)
 
