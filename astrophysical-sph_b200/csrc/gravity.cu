@@ -586,11 +586,12 @@ cudaError_t sph_launch_walk(sph_handle *h) {
     }
     const double th2 = h->p.theta * h->p.theta;
     double *out = h->walk_buf + (size_t)h->rank * 4 * h->walk_chunk;
-    // block rows = work items per tile (the root's children are dealt to them).  One GPU: 2 rows (the child that
-    // contains the tile | the 7 others); several ranks: 8 (a rank then owns about one wave of tiles).  SPH_B200_WALK_ROWS
-    // overrides (1..8).  With one row the kernel writes its sums straight into walk_buf.
+    // block rows = work items per tile (the root's children are dealt to them): 8 - with more, shorter items the tail of
+    // the launch stays short when the grid is only a wave or two of blocks (N = 1e5 on one GPU: 1.08 vs 1.50 ms with 2
+    // rows; at N = 1e6 1..8 rows measure the same).  SPH_B200_WALK_ROWS overrides (1..8); with one row the kernel
+    // writes its sums straight into walk_buf.
     static const int rows_env = getenv("SPH_B200_WALK_ROWS") ? atoi(getenv("SPH_B200_WALK_ROWS")) : 0;
-    int rows = rows_env > 0 ? rows_env : (h->nranks > 1 ? 8 : 2);
+    int rows = rows_env > 0 ? rows_env : 8;
     rows = rows < 1 ? 1 : (rows > 8 ? 8 : rows);
     double *part = rows == 1 ? out : h->walk_part;
     const dim3 grid((unsigned)blocks, (unsigned)rows);

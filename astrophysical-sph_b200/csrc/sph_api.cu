@@ -59,6 +59,11 @@ cudaError_t dalloc(T **p, size_t n) {
     return cudaMalloc((void **)p, n * sizeof(T) + 256);
 }
 
+void drop_step_graph(sph_handle *h) {
+    if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+    h->step_graph = nullptr;
+}
+
 // grow-only device scratch of the handle (getters, density_at): no cudaMalloc / cudaFree per call
 int ensure_scratch(sph_handle *h, size_t bytes) {
     if (bytes <= h->scratch_bytes) return SPH_OK;
@@ -130,6 +135,7 @@ int check_flags(sph_handle *h) {
         cudaMemsetAsync(h->scal + SC_STICKY, 0, sizeof(unsigned long long), h->stream);
         // the failed evaluation left stale results behind: nothing of it may be read or used as a search hint
         h->have_eval = false; h->lists_valid = false; h->hint_valid = false; h->outputs_fresh = false;
+        drop_step_graph(h);
         if (f & ERRF_DEPTH)
             return sph_fail(h, SPH_ERR_TREE_DEPTH,
                             "octree: two particles share all " + std::to_string(SPH_LEVELS) + " octant levels (coincident particles?); "
@@ -289,6 +295,28 @@ __global__ void upload_unpack_kernel(int64_t N, int64_t per, int ncol, const dou
         vel[i] = src[3 * per]; vel[i + N] = src[4 * per]; vel[i + 2 * N] = src[5 * per];
         if (ncol == 7) kent[i] = src[6 * per];
     }
+}
+
+// One iteration of the reference's `while t < tEnd` body on the uploaded state, enqueued on the handle's stream:
+// getAcc, adaptive dt, statistics row (-> log_row, 11 doubles), predictor, getAcc at the half step, corrector,
+// t += dt; evolve_K! twice for the polytropic EOS.   F/isothermal_sim.jl:155-212, F/polytrope_sim.jl:162-231
+int enqueue_step(sph_handle *h, double *log_row) {
+    const bool poly = h->p.eos == SPH_EOS_POLYTROPIC;
+    // getAcc #1, dt, statistics                                   F/isothermal_sim.jl:155-192
+    if (int rc = eval_internal(h, h->pos, h->vel, poly ? h->kent : nullptr, h->acc)) return rc;
+    cudaError_t e = sph_launch_dt(h);
+    if (e == cudaSuccess) e = sph_launch_stats(h, log_row);
+    // predictor                                                   :197-200
+    if (e == cudaSuccess) e = sph_launch_predict(h);
+    if (e == cudaSuccess && poly) e = sph_launch_evolve_k(h);      // F/polytrope_sim.jl:217
+    if (e != cudaSuccess) return sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e));
+    // getAcc #2 at the half step                                  :203
+    if (int rc = eval_internal(h, h->pos_half, h->vel_half, poly ? h->kent : nullptr, h->acc)) return rc;
+    if (poly) e = sph_launch_evolve_k(h);                           // F/polytrope_sim.jl:221
+    // corrector, t += dt                                           :206-212
+    if (e == cudaSuccess) e = sph_launch_correct(h);
+    if (e != cudaSuccess) return sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e));
+    return SPH_OK;
 }
 
 int d2h(sph_handle *h, double *dst, const double *src, size_t n) {
@@ -468,6 +496,7 @@ int sph_destroy(sph_handle *h) {
                     h->tree.bfs_of_old, h->tree.level_start};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    drop_step_graph(h);
     if (h->scratch) cudaFree(h->scratch);
     if (h->log_dev) cudaFree(h->log_dev);
     if (h->h_log) cudaFreeHost(h->h_log);
@@ -493,6 +522,7 @@ int sph_set_stream(sph_handle *h, void *cuda_stream) {
     if (!h) return SPH_ERR_INVALID;
     SPH_CUDA(h, cudaSetDevice(h->p.device));
     SPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    drop_step_graph(h);
     if (cuda_stream) {
         if (h->own_stream) cudaStreamDestroy(h->stream);
         h->stream = (cudaStream_t)cuda_stream;
@@ -593,37 +623,60 @@ int sph_step(sph_handle *h, int nsteps, sph_step_info *info) {
     if (!h->have_state) return sph_fail(h, SPH_ERR_STATE, "sph_step: no state uploaded");
     if (nsteps == 0) return SPH_OK;
     SPH_CUDA(h, cudaSetDevice(h->p.device));
-    const bool poly = h->p.eos == SPH_EOS_POLYTROPIC;
     // step log {dt, stats row} x nsteps: device buffer + pinned mirror owned by the handle (grown on demand)
-    if ((size_t)nsteps > h->log_cap) {
+    if ((size_t)nsteps + 1 > h->log_cap) {
         SPH_CUDA(h, cudaStreamSynchronize(h->stream));
         if (h->log_dev) cudaFree(h->log_dev);
         if (h->h_log) cudaFreeHost(h->h_log);
         h->log_dev = nullptr; h->h_log = nullptr; h->log_cap = 0;
-        const size_t cap = (size_t)nsteps < 256 ? 256 : (size_t)nsteps;
+        drop_step_graph(h);                        // it wrote into the old buffer
+        const size_t cap = (size_t)nsteps + 1 < 256 ? 256 : (size_t)nsteps + 1;
         SPH_CUDA(h, cudaMalloc((void **)&h->log_dev, cap * 11 * sizeof(double)));
         SPH_CUDA(h, cudaMallocHost((void **)&h->h_log, cap * 11 * sizeof(double)));
         h->log_cap = cap;
     }
     double *log_dev = h->log_dev;
+    double *graph_row = log_dev + (h->log_cap - 1) * 11;      // the captured step writes its row here
+    // Small problems are bound by launch latency (N = 5 000: ~135 launches of a few microseconds each per step): once the
+    // handle has search hints, ONE step is captured into a CUDA graph and replayed.  Single GPU, N <= SPH_B200_GRAPH_N
+    // (default 262 144; 0 disables).  The phase timers are not recorded during a replay (sph_get_timings then fails).
+    static const int64_t graph_n = getenv("SPH_B200_GRAPH_N") ? atoll(getenv("SPH_B200_GRAPH_N")) : 262144;
+    static const bool trace = getenv("SPH_B200_TRACE") != nullptr;
     int rc = SPH_OK;
     for (int s = 0; s < nsteps && rc == SPH_OK; ++s) {
-        // getAcc #1, dt, statistics                                   F/isothermal_sim.jl:155-192
-        rc = eval_internal(h, h->pos, h->vel, poly ? h->kent : nullptr, h->acc);
-        if (rc) break;
-        cudaError_t e = sph_launch_dt(h);
-        if (e == cudaSuccess) e = sph_launch_stats(h, log_dev + (size_t)s * 11);
-        // predictor                                                   :197-200
-        if (e == cudaSuccess) e = sph_launch_predict(h);
-        if (e == cudaSuccess && poly) e = sph_launch_evolve_k(h);      // F/polytrope_sim.jl:217
+        const bool use_graph = h->nranks == 1 && h->N <= graph_n && h->hint_valid && !h->no_hint && !trace;
+        if (!use_graph) {
+            rc = enqueue_step(h, log_dev + (size_t)s * 11);
+            continue;
+        }
+        if (!h->step_graph) {
+            const long long l0 = g_sph_launches;
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                rc = enqueue_step(h, graph_row);
+                e = cudaStreamEndCapture(h->stream, &g);
+                if (rc != SPH_OK) e = cudaErrorUnknown;
+            }
+            h->graph_launches = g_sph_launches - l0;
+            g_sph_launches = l0;                                  // nothing ran yet
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&h->step_graph, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                h->step_graph = nullptr;
+                if (rc == SPH_OK) rc = sph_fail(h, SPH_ERR_CUDA, std::string("sph_step: graph capture failed: ") + cudaGetErrorString(e));
+                break;
+            }
+        }
+        cudaError_t e = cudaGraphLaunch(h->step_graph, h->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(log_dev + (size_t)s * 11, graph_row, 11 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
         if (e != cudaSuccess) { rc = sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e)); break; }
-        // getAcc #2 at the half step                                  :203
-        rc = eval_internal(h, h->pos_half, h->vel_half, poly ? h->kent : nullptr, h->acc);
-        if (rc) break;
-        if (poly) e = sph_launch_evolve_k(h);                           // F/polytrope_sim.jl:221
-        // corrector, t += dt                                           :206-212
-        if (e == cudaSuccess) e = sph_launch_correct(h);
-        if (e != cudaSuccess) { rc = sph_fail(h, SPH_ERR_CUDA, cudaGetErrorString(e)); break; }
+        sph_note((int)h->graph_launches);
+        h->ev_valid = false;              // the timing events of a captured step are dependencies, not records
+        h->have_eval = true; h->lists_valid = true; h->hint_valid = true; h->outputs_fresh = false;
+        h->last_acc = h->acc;
     }
     if (rc == SPH_OK && info) {
         cudaError_t e = cudaMemcpyAsync(h->h_log, log_dev, (size_t)nsteps * 11 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
@@ -719,7 +772,9 @@ int sph_get_octree(sph_handle *h, double *nodes, int64_t cap, int64_t *n_nodes) 
 
 int sph_get_timings(sph_handle *h, sph_timings *out) {
     if (!h || !out) return SPH_ERR_INVALID;
-    if (!h->ev_valid) return sph_fail(h, SPH_ERR_STATE, "sph_get_timings: no force evaluation yet");
+    if (!h->ev_valid)
+        return sph_fail(h, SPH_ERR_STATE, "sph_get_timings: no timed force evaluation (none yet, or the last step was replayed "
+                                          "as a CUDA graph: SPH_B200_GRAPH_N=0 disables that)");
     SPH_CUDA(h, cudaSetDevice(h->p.device));
     SPH_CUDA(h, cudaEventSynchronize(h->ev[PH_COUNT]));
     float ms[PH_COUNT];
@@ -813,6 +868,7 @@ int sph_comm_init(sph_handle *h, int nranks, int rank, const void *id128) {
     ncclComm_t comm;
     SPH_NCCL(h, nc.CommInitRank(&comm, nranks, id, rank));
     h->nccl = comm;
+    drop_step_graph(h);
     set_partition(h, nranks, rank);
     h->have_eval = false; h->lists_valid = false; h->hint_valid = false;
     // pairs {target of another rank, reverse partner}: each rank contributes up to 2 * chunk of them per evaluation

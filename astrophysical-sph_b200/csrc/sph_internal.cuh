@@ -219,6 +219,8 @@ struct sph_handle {
     double *red_partial = nullptr;         // per-block partial sums of the statistics kernels
     double *log_dev = nullptr, *h_log = nullptr;   // step log {dt, stats row} of sph_step: device + pinned mirror
     size_t log_cap = 0;                            // steps
+    cudaGraphExec_t step_graph = nullptr;          // one captured step (small N: launch-latency bound), see sph_step
+    long long graph_launches = 0;                  // kernels in it
     void *scratch = nullptr;                       // grow-only scratch of the getters / density_at
     size_t scratch_bytes = 0;
     // timing

@@ -483,13 +483,13 @@ def test_run_simulation_writes_reference_files(sph, oracle, tmp_path):
 
 @pytest.mark.parametrize("env", ["SPH_B200_WALK_DFS=1", "SPH_B200_WALK_T=1", "SPH_B200_WALK_ROWS=1", "SPH_B200_NO_OVERLAP=1",
                                  "SPH_B200_KNN_SORT=1", "SPH_B200_NO_HINT=1", "SPH_B200_SPH_TILE=1", "SPH_B200_SPH_TILE=0",
-                                 "SPH_B200_ECAP=8", "SPH_B200_WALK_FORCE_DEEP=1"])
+                                 "SPH_B200_ECAP=8", "SPH_B200_WALK_FORCE_DEEP=1", "SPH_B200_GRAPH_N=0"])
 def test_alternative_paths_agree(sph, env):
     """Every switchable kernel variant (shared walk without the pair queue, pair queue for single-lane cells only, one
     block row per tile, serial force / walk, sorted instead of selected hits, unhinted search, shared-memory tile /
     direct-gather SPH sums, an 8-entry extras table that sends reverse partners through the overflow list, the
-    42-level walk variant that takes over when the regular walk's stack overflows) passes the same two-step parity
-    check against the oracle."""
+    42-level walk variant that takes over when the regular walk's stack overflows, plain launches instead of the CUDA
+    graph replay that small problems use) passes the same two-step parity check against the oracle."""
     import subprocess
     import sys
 
