@@ -219,6 +219,34 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int 
             }
         }
     }
+    // first all the slot requests of up to 8 entries (independent atomics: one round trip instead of one per entry),
+    // then the stores; whatever is left takes the plain path
+    {
+        int tj[8], slot[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            tj[u] = -1; slot[u] = 0;
+            if (defer) {
+                const int j = __ffsll((long long)defer) - 1;
+                defer &= defer - 1ull;
+                const int nj = lst[j * lstride];
+                if (nj >= x.own0 && nj < x.own1) { tj[u] = nj; slot[u] = atomicAdd(&x.ecnt[nj], 1); }
+                else push_extra(x, nj, (int)s, scal);             // another rank's particle: exchange buffer
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (tj[u] >= 0) {
+                if (slot[u] < x.ecap) {
+                    x.ext[(int64_t)slot[u] * x.NL + tj[u]] = (int)s;
+                } else {
+                    const unsigned long long o = atomicAdd(scal + SC_OVF, 1ull);
+                    if (o < (unsigned long long)x.ovcap) x.ovf[o] = make_int2(tj[u], (int)s);
+                    else atomicOr(scal + SC_ERR, (unsigned long long)ERRF_EXTRAS);
+                }
+            }
+        }
+    }
     while (defer) {
         const int j = __ffsll((long long)defer) - 1;
         defer &= defer - 1ull;
