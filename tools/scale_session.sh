@@ -10,7 +10,7 @@ for spec in "$@"; do
     echo "rc=$? $out: $(python -c "
 import json,sys
 try:
-    d=json.load(open('$out.json'))
+    d=json.loads([l for l in open('$out.json') if l.startswith('{')][-1])
     print('N=%d %.3f ms/step value %.4g e2e %.4g comm %.3f parity_ok=%s' % (d['config']['N'], d['ms_per_step'], d['value'], d['e2e']['value'], d.get('comm_ms_last_eval') or 0, (d.get('parity') or {}).get('ok')))
 except Exception as e:
     print('no line', e)
