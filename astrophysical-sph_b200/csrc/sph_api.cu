@@ -871,8 +871,11 @@ int sph_comm_init(sph_handle *h, int nranks, int rank, const void *id128) {
     drop_step_graph(h);
     set_partition(h, nranks, rank);
     h->have_eval = false; h->lists_valid = false; h->hint_valid = false;
-    // pairs {target of another rank, reverse partner}: each rank contributes up to 2 * chunk of them per evaluation
-    h->obcap = 2 * h->chunk;
+    // pairs {target of another rank, reverse partner} a rank may contribute per evaluation.  They come from the surface
+    // of the rank's key range: 2.0e4 .. 2.7e4 per rank at N = 1e6 for 2 .. 16 ranks (0.05 .. 0.33 of the targets per
+    // rank), growing like N^(2/3).  The buffer is all-gathered in full every evaluation, so it is sized with a
+    // margin of ~3 instead of for the worst case; an overflow is reported (ERRF_HALO), never silently dropped.
+    h->obcap = h->chunk / 2 > 65536 ? h->chunk / 2 : 65536;
     if (const char *e = getenv("SPH_B200_HALO_CAP")) h->obcap = atoll(e) > 1024 ? atoll(e) : 1024;
     SPH_CUDA(h, dalloc(&h->outbox, (size_t)h->obcap + 1));
     SPH_CUDA(h, dalloc(&h->inbox, (size_t)nranks * ((size_t)h->obcap + 1)));
