@@ -111,7 +111,7 @@ __device__ __forceinline__ bool walk_skipped(const unsigned long long *__restric
 template <bool COUNT, bool DEEP>
 __global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : 8) walk_kernel(int64_t N, int nranks, int rank, int64_t chunk,
                                                                  const double4 *__restrict__ pos4,
-                                                                 const double2 *__restrict__ hr, SphTree t,
+                                                                 const double *__restrict__ hs, SphTree t,
                                                                  double theta_sq, double m,
                                                                  unsigned long long *__restrict__ scal,
                                                                  double *__restrict__ part /* [8][4][chunk] */) {
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : 8) walk_kernel(int64
     double px = 0, py = 0, pz = 0, hi = 1.0;
     if (active) {
         const double4 p = pos4[s];
-        px = p.x; py = p.y; pz = p.z; hi = hr[s].x;
+        px = p.x; py = p.y; pz = p.z; hi = hs[s];
     }
     const double hi2 = hi * hi;
     const double h2x = 2.0 * hi * (1.0 + 1e-9);      // clause 2 is certainly true when mindist > h2x
@@ -331,7 +331,7 @@ __device__ __forceinline__ void leaf_pair(double d_sq, double hi, double hj, dou
 template <bool COUNT, bool DEEP>
 __global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : WALK_MINB) walk_pairs_kernel(int64_t N, int nranks, int rank, int64_t chunk,
                                                                        const double4 *__restrict__ pos4,
-                                                                       const double2 *__restrict__ hr, SphTree t,
+                                                                       const double *__restrict__ hs, SphTree t,
                                                                        double theta_sq, double th_lo, double th_hi, double m,
                                                                        int sparse_t, unsigned long long *__restrict__ scal,
                                                                        double *__restrict__ part /* [8][4][chunk] */) {
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : WALK_MINB) walk_pair
     double px = 0, py = 0, pz = 0, hi = 1.0;
     if (active) {
         const double4 p = pos4[s];
-        px = p.x; py = p.y; pz = p.z; hi = hr[s].x;
+        px = p.x; py = p.y; pz = p.z; hi = hs[s];
     }
     const int sbase = (int)(s - lane);               // sorted slot of lane 0's target
     const double hi2 = hi * hi;
@@ -555,14 +555,14 @@ __global__ void walk_reduce_kernel(int64_t n4 /* 4 * chunk */, int rows, const d
 }
 
 // after the search: one 64-byte walk record per node (leaves carry h_j instead of their constant mass m)
-__global__ void pack_nodes_kernel(SphTree t, const double2 *__restrict__ hr, const unsigned long long *__restrict__ scal) {
+__global__ void pack_nodes_kernel(SphTree t, const double *__restrict__ hs, const unsigned long long *__restrict__ scal) {
     if (scal[SC_ERR] != 0ull) return;
     const int64_t M = (int64_t)scal[SC_NNODES];
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < M; k += (int64_t)gridDim.x * blockDim.x) {
         const int2 I = t.nodeI[k];
         double4 A = t.nodeA[k];
         double2 D = make_double2(0.0, 0.0);
-        if (I.y == 0) A.w = hr[I.x].x;
+        if (I.y == 0) A.w = hs[I.x];
         else D = t.nodeD[k];
         double4 *rec = t.nodeW + GW_REC * k;
         rec[0] = A;
@@ -575,7 +575,7 @@ __global__ void pack_nodes_kernel(SphTree t, const double2 *__restrict__ hr, con
 cudaError_t sph_launch_walk(sph_handle *h) {
     static_assert(GW_WARPS * 32 == 128, "walk tiles are 128 targets (finish_kernel and sph_comm_init assume it)");
     sph_note(1);
-    pack_nodes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->tree, h->hr, h->scal);
+    pack_nodes_kernel<<<148 * 8, 256, 0, h->stream>>>(h->tree, h->hs, h->scal);
     const int64_t tiles = (h->N + 127) / 128;
     const int64_t groups = (tiles + SPH_WALK_DEAL - 1) / SPH_WALK_DEAL;
     const int64_t blocks = (groups - h->rank + h->nranks - 1) / h->nranks * SPH_WALK_DEAL;   // groups rank, rank + P, ...
@@ -612,11 +612,11 @@ cudaError_t sph_launch_walk(sph_handle *h) {
 #define WALK_LAUNCH(DEEP)                                                                                                       \
     do {                                                                                                                        \
         if (shared) {                                                                                                           \
-            if (count) walk_kernel<true, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree, th2, h->p.m, h->scal, part);   \
-            else walk_kernel<false, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree, th2, h->p.m, h->scal, part);        \
+            if (count) walk_kernel<true, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, h->p.m, h->scal, part);   \
+            else walk_kernel<false, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, h->p.m, h->scal, part);        \
         } else {                                                                                                                \
-            if (count) walk_pairs_kernel<true, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree, th2, lo, hi, h->p.m, sparse_t, h->scal, part);   \
-            else walk_pairs_kernel<false, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hr, h->tree, th2, lo, hi, h->p.m, sparse_t, h->scal, part);        \
+            if (count) walk_pairs_kernel<true, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, lo, hi, h->p.m, sparse_t, h->scal, part);   \
+            else walk_pairs_kernel<false, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, lo, hi, h->p.m, sparse_t, h->scal, part);        \
         }                                                                                                                       \
     } while (0)
     WALK_LAUNCH(false);

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int 
                                                       const double4 *__restrict__ vel4, double cs, double gamma,
                                                       double2 *__restrict__ hr, double4 *__restrict__ pc) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    if (scal[SC_ERR] != 0ull) return;
+    if (SPH_ERR_BLOCKING(scal) != 0ull) return;
     const int64_t s0 = t0 + (int64_t)blockIdx.x * HB;
     const int64_t s = s0 + threadIdx.x;
     // ---- staging
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int 
 // extras of other ranks' targets that point into this rank's range: append them (order is fixed afterwards)
 __global__ void __launch_bounds__(256) extras_merge_kernel(const int2 *__restrict__ inbox, int nranks, int rank, int64_t stride,
                                                             ExtrasOut x, unsigned long long *__restrict__ scal) {
-    if (scal[SC_ERR] != 0ull) return;
+    if (SPH_ERR_BLOCKING(scal) != 0ull) return;
     for (int r = 0; r < nranks; ++r) {
         if (r == rank) continue;
         const int2 *box = inbox + (int64_t)r * stride;
@@ -280,7 +280,7 @@ __global__ void outbox_header_kernel(int2 *__restrict__ outbox, int obcap, const
 __global__ void __launch_bounds__(HB) extras_sort_kernel(int64_t NL, int64_t t0, int64_t t1, int ecap,
                                                           const int *__restrict__ ecnt, int *__restrict__ ext,
                                                           const unsigned long long *__restrict__ scal) {
-    if (scal[SC_ERR] != 0ull) return;
+    if (SPH_ERR_BLOCKING(scal) != 0ull) return;
     const int64_t s = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= t1) return;
     int n = ecnt[s];
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(HB) eos_kernel(int64_t N, const double *__rest
                                                   const double4 *__restrict__ vel4, int poly, double cs, double gamma,
                                                   const unsigned long long *__restrict__ scal, double2 *__restrict__ hr,
                                                   double4 *__restrict__ pc) {
-    if (scal[SC_ERR] != 0ull) return;
+    if (SPH_ERR_BLOCKING(scal) != 0ull) return;
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
     const double h = sqrt(pos4[s].w) / 2;            // h = r[:, end] ./ 2   (:151)
@@ -329,11 +329,13 @@ __global__ void __launch_bounds__(HB) eos_kernel(int64_t N, const double *__rest
 // K-th distance of every neighbour next to its position; also clears the extras counters
 __global__ void __launch_bounds__(HB) smoothing_kernel(int64_t N, const double *__restrict__ d2k,
                                                         const unsigned long long *__restrict__ scal,
-                                                        double4 *__restrict__ pos4, int *__restrict__ ecnt) {
-    if (scal[SC_ERR] != 0ull) return;
+                                                        double4 *__restrict__ pos4, double *__restrict__ hs, int *__restrict__ ecnt) {
+    if (SPH_ERR_BLOCKING(scal) != 0ull) return;
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
-    pos4[s].w = d2k[s];
+    const double v = d2k[s];
+    pos4[s].w = v;
+    hs[s] = sqrt(v) / 2;                             // h = r[:, end] ./ 2   (:151): the tree walk starts from it
     ecnt[s] = 0;
 }
 
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int6
                                                     double *__restrict__ ahyd, double *__restrict__ dkdt,
                                                     double *__restrict__ sumvdw, double *__restrict__ mumax) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    if (scal[SC_ERR] != 0ull) return;
+    if (SPH_ERR_BLOCKING(scal) != 0ull) return;
     const int64_t s0 = t0 + (int64_t)blockIdx.x * HB;
     const int64_t s = s0 + threadIdx.x;
     const int *lst = nbr + s;
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(HB) force_overflow_kernel(int64_t NS, int64_t 
                                                              int ecap, const int2 *__restrict__ ovf, int ovcap, double m,
                                                              double alpha, double beta, const unsigned long long *__restrict__ scal,
                                                              double *__restrict__ ahyd, double *__restrict__ dkdt) {
-    if (scal[SC_ERR] != 0ull) return;
+    if (SPH_ERR_BLOCKING(scal) != 0ull) return;
     const unsigned long long no = scal[SC_OVF];
     if (no == 0ull) return;
     const int n = (int)(no < (unsigned long long)ovcap ? no : (unsigned long long)ovcap);
@@ -551,7 +553,7 @@ static bool use_tile_kernels() {
 
 cudaError_t sph_launch_smoothing(sph_handle *h) {
     sph_note(1);
-    smoothing_kernel<<<(int)((h->N + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->d2k, h->scal, h->pos4, h->ecnt);
+    smoothing_kernel<<<(int)((h->N + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->d2k, h->scal, h->pos4, h->hs, h->ecnt);
     return cudaGetLastError();
 }
 

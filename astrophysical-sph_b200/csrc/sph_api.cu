@@ -195,8 +195,10 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     SPH_CUDA(h, sph_launch_knn(h, t0, t1));
     TRACE("sph_launch_knn done");
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_KNN + 1], st));
-    // ---- density + EOS phase
-    if (multi) {   // list membership tests and the smoothing lengths need the K-th distance of every particle
+    // ---- K-th distances of all particles (list membership tests, smoothing lengths), then the evaluation forks:
+    //   second stream  density -> [rho + cross-rank reverse pairs all-gathered] -> EOS -> force -> [force outputs all-gathered]
+    //   main stream    tree walk (needs h only) -> [g, PHI all-gathered]
+    if (multi) {
         SPH_CUDA(h, cudaEventRecord(h->cev[0], st));
         SPH_NCCL(h, nc.GroupStart());
         SPH_NCCL(h, nc.AllGather(h->d2k + h->rank * chunk, h->d2k, (size_t)chunk, ncclDouble, comm, st));
@@ -205,37 +207,45 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
         SPH_CUDA(h, cudaEventRecord(h->cev[1], st));
     }
     SPH_CUDA(h, sph_launch_smoothing(h));
-    SPH_CUDA(h, sph_launch_density(h, t0, t1, !multi));
-    TRACE("sph_launch_density done");
-    if (multi) {   // rho of all particles; reverse pairs that point at other ranks' targets
-        SPH_CUDA(h, sph_launch_outbox_header(h));
-        SPH_CUDA(h, cudaEventRecord(h->cev[2], st));
-        SPH_NCCL(h, nc.GroupStart());
-        SPH_NCCL(h, nc.AllGather(h->rho_s + h->rank * chunk, h->rho_s, (size_t)chunk, ncclDouble, comm, st));
-        SPH_NCCL(h, nc.AllGather(h->outbox, h->inbox, (size_t)(h->obcap + 1) * 2, ncclInt32, comm, st));
-        SPH_NCCL(h, nc.GroupEnd());
-        SPH_CUDA(h, cudaEventRecord(h->cev[3], st));
-        SPH_CUDA(h, sph_launch_extras_merge(h, t0, t1));
-        SPH_CUDA(h, sph_launch_eos(h));
-        TRACE("sph_launch_eos done");
-    }
-    SPH_CUDA(h, sph_launch_extras_sort(h, t0, t1));
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_DENSITY + 1], st));
-    // ---- force (second stream when overlapping) || walk (main stream)
     const bool ov = h->overlap && (!multi || h->nccl2 != nullptr);
     cudaStream_t fs = ov ? h->stream2 : st;
+    ncclComm_t fc = ov ? (ncclComm_t)h->nccl2 : comm;
     if (ov) {
         SPH_CUDA(h, cudaEventRecord(h->ev_fork, st));
         SPH_CUDA(h, cudaStreamWaitEvent(fs, h->ev_fork, 0));
     }
-    SPH_CUDA(h, cudaEventRecord(h->fev[0], fs));
+    SPH_CUDA(h, cudaEventRecord(h->dev[0], fs));
     h->stream = fs;                       // the launch helpers enqueue on h->stream
-    cudaError_t fe = sph_launch_force(h, t0, t1);
+    cudaError_t fe = sph_launch_density(h, t0, t1, !multi);
+    if (fe == cudaSuccess && multi) fe = sph_launch_outbox_header(h);
+    h->stream = st;
+    SPH_CUDA(h, fe);
+    TRACE("sph_launch_density done");
+    if (multi) {   // rho of all particles; reverse pairs that point at other ranks' targets
+        SPH_CUDA(h, cudaEventRecord(h->cev[2], fs));
+        SPH_NCCL(h, nc.GroupStart());
+        SPH_NCCL(h, nc.AllGather(h->rho_s + h->rank * chunk, h->rho_s, (size_t)chunk, ncclDouble, fc, fs));
+        SPH_NCCL(h, nc.AllGather(h->outbox, h->inbox, (size_t)(h->obcap + 1) * 2, ncclInt32, fc, fs));
+        SPH_NCCL(h, nc.GroupEnd());
+        SPH_CUDA(h, cudaEventRecord(h->cev[3], fs));
+    }
+    h->stream = fs;
+    if (multi) {
+        fe = sph_launch_extras_merge(h, t0, t1);
+        if (fe == cudaSuccess) fe = sph_launch_eos(h);
+    }
+    if (fe == cudaSuccess) fe = sph_launch_extras_sort(h, t0, t1);
+    h->stream = st;
+    SPH_CUDA(h, fe);
+    SPH_CUDA(h, cudaEventRecord(h->dev[1], fs));
+    SPH_CUDA(h, cudaEventRecord(h->fev[0], fs));
+    h->stream = fs;
+    fe = sph_launch_force(h, t0, t1);
     h->stream = st;
     SPH_CUDA(h, fe);
     TRACE("sph_launch_force done");
     if (multi) {
-        ncclComm_t fc = ov ? (ncclComm_t)h->nccl2 : comm;
         SPH_CUDA(h, cudaEventRecord(h->cev[4], fs));
         SPH_NCCL(h, nc.GroupStart());
         for (int c = 0; c < 6; ++c)
@@ -424,7 +434,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(dalloc(&h->o_g, 3 * N));
     CK(dalloc(&h->keys, N)); CK(dalloc(&h->keys_alt, N)); CK(dalloc(&h->klo, N)); CK(dalloc(&h->perm, N)); CK(dalloc(&h->perm_alt, N));
     CK(dalloc(&h->pos4, NS)); CK(dalloc(&h->vel4, NS)); CK(dalloc(&h->hr, NS)); CK(dalloc(&h->pc, NS));
-    CK(dalloc(&h->rho_s, NS)); CK(dalloc(&h->d2k, NS)); CK(dalloc(&h->kid, NS)); CK(dalloc(&h->nbr, NL * K));
+    CK(dalloc(&h->rho_s, NS)); CK(dalloc(&h->hs, NS)); CK(dalloc(&h->d2k, NS)); CK(dalloc(&h->kid, NS)); CK(dalloc(&h->nbr, NL * K));
     CK(dalloc(&h->ecnt, NL)); CK(dalloc(&h->ext, NL * (size_t)SPH_ECAP));
     h->ovcap = (int64_t)(N / 4 > 65536 ? N / 4 : 65536);
     CK(dalloc(&h->ovf, (size_t)h->ovcap));
@@ -473,6 +483,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->fev[0])); CK(cudaEventCreate(&h->fev[1]));
+    CK(cudaEventCreate(&h->dev[0])); CK(cudaEventCreate(&h->dev[1]));
     h->overlap = getenv("SPH_B200_NO_OVERLAP") == nullptr;
     CK(cudaDeviceSynchronize());
 #undef CK
@@ -489,7 +500,7 @@ int sph_destroy(sph_handle *h) {
     void *ptrs[] = {h->pos, h->vel, h->kent, h->acc, h->pos_half, h->vel_half, h->in_pos, h->in_vel, h->in_kent,
                     h->in_acc, h->o_rho, h->o_h, h->o_phi, h->o_sumvdw, h->o_mumax, h->o_cs, h->o_dkdt, h->o_ahyd,
                     h->o_g, h->keys, h->keys_alt, h->klo, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->pc,
-                    h->rho_s, h->d2k, h->kid, h->nbr, h->ecnt, h->ext, h->ovf, h->outbox, h->inbox, h->s_red, h->walk_buf, h->walk_part, h->cnt,
+                    h->rho_s, h->hs, h->d2k, h->kid, h->nbr, h->ecnt, h->ext, h->ovf, h->outbox, h->inbox, h->s_red, h->walk_buf, h->walk_part, h->cnt,
                     h->base, h->scal, h->stat_dev, h->red_partial, h->tree.nodeI, h->tree.nodeA, h->tree.nodeB,
                     h->tree.nodeC, h->tree.nodeD, h->tree.nodeW, h->tree.nodeBC, h->tree.parent, h->tree.arrive, h->tree.leaf_of, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,
                     h->tree.old_depth, h->tree.dkey_in, h->tree.dkey_out, h->tree.dval_in, h->tree.dval_out,
@@ -513,6 +524,8 @@ int sph_destroy(sph_handle *h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int i = 0; i < 2; ++i)
         if (h->fev[i]) cudaEventDestroy(h->fev[i]);
+    for (int i = 0; i < 2; ++i)
+        if (h->dev[i]) cudaEventDestroy(h->dev[i]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SPH_OK;
@@ -780,7 +793,11 @@ int sph_get_timings(sph_handle *h, sph_timings *out) {
     float ms[PH_COUNT];
     for (int i = 0; i < PH_COUNT; ++i) SPH_CUDA(h, cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
     out->sort_ms = ms[PH_SORT]; out->tree_ms = ms[PH_TREE]; out->knn_ms = ms[PH_KNN];
-    out->density_ms = ms[PH_DENSITY];
+    {   // density + EOS (+ their all-gather) and the force are measured on the stream they ran on (beside the walk)
+        float f = 0.f;
+        SPH_CUDA(h, cudaEventElapsedTime(&f, h->dev[0], h->dev[1]));
+        out->density_ms = ms[PH_DENSITY] + f;
+    }
     {   // the force phase is measured on the stream it ran on (it overlaps the walk)
         float f = 0.f;
         SPH_CUDA(h, cudaEventElapsedTime(&f, h->fev[0], h->fev[1]));

@@ -192,6 +192,7 @@ struct sph_handle {
     double2 *hr = nullptr;      // {h, rho}
     double4 *pc = nullptr;      // {rho, P/rho^2, h, c}: the record the force pass gathers per neighbour
     double *rho_s = nullptr;    // density of the owned targets (all-gathered in multi-GPU runs)
+    double *hs = nullptr;       // smoothing length of every particle, set right after the search (the walk starts from it)
     double *d2k = nullptr;      // K-th squared distance
     int *kid = nullptr;         // caller's id of the K-th list entry when the K-th distance is tied, else INT_MAX
     int *nbr = nullptr;         // K x NL
@@ -230,7 +231,7 @@ struct sph_handle {
     // the force kernel (+ its all-reduce) runs on a second stream, concurrently with the tree walk: both only need
     // the density/EOS results, and the latency-bound force kernel fills the issue slots the walk's tail leaves idle
     cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, fev[2]{};   // fev: force phase on the stream it ran on
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, fev[2]{}, dev[2]{};   // fev / dev: force and density phases on the stream they ran on
     void *nccl2 = nullptr;  // communicator of stream2 (NCCL calls of one communicator must not run concurrently)
     bool overlap = true;
     bool ev_valid = false;
@@ -242,6 +243,9 @@ struct sph_handle {
 
 // scal[0..SC_RESET) is cleared at the start of every force evaluation; SC_STICKY accumulates error flags
 enum { SC_LDOM = 0, SC_NNODES, SC_ERR, SC_DT, SC_VISITS, SC_KNN_RETRY, SC_OVF, SC_OUTBOX, SC_RESET = 15, SC_STICKY = 15, SC_COUNT = 16 };
+// ERRF_STACK is transient: the regular walk raises it, the DEEP walk variant answers and clears it (gravity.cu).  Kernels
+// that run beside the walk (density, force on the second stream) must not mistake it for a failed evaluation.
+#define SPH_ERR_BLOCKING(scal) ((scal)[SC_ERR] & ~(unsigned long long)ERRF_STACK)
 enum { ERRF_DEPTH = 1, ERRF_NODES = 2, ERRF_STACK = 4, ERRF_NAN = 8, ERRF_EXTRAS = 16, ERRF_HALO = 32, ERRF_STACK2 = 64 };
 
 int sph_fail(sph_handle *h, int code, const std::string &msg);
