@@ -108,22 +108,17 @@ __device__ __forceinline__ bool walk_skipped(const unsigned long long *__restric
     return DEEP ? f != (unsigned long long)ERRF_STACK : f != 0ull;
 }
 
-template <bool COUNT, bool DEEP>
-__global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : 8) walk_kernel(int64_t N, int nranks, int rank, int64_t chunk,
-                                                                 const double4 *__restrict__ pos4,
-                                                                 const double *__restrict__ hs, SphTree t,
-                                                                 double theta_sq, double m,
-                                                                 unsigned long long *__restrict__ scal,
-                                                                 double *__restrict__ part /* [8][4][chunk] */) {
-    constexpr int STACK = DEEP ? GW_STACK_DEEP : GW_STACK;
-    __shared__ int4 s_stack[GW_WARPS][STACK];   // {first child, nch | leafmask << 8, lane mask, -}
-    if (walk_skipped<DEEP>(scal)) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int4 *stack = s_stack[warp];
+// one work item (tile bx of this rank, block row `row` of `rows`) of the shared walk
+template <bool COUNT, bool DEEP, int STACK>
+__device__ __forceinline__ void walk_tile(int bx, int row, int rows, int4 *__restrict__ stack, int64_t N, int nranks, int rank,
+                                          int64_t chunk, const double4 *__restrict__ pos4, const double *__restrict__ hs,
+                                          const SphTree &t, double theta_sq, double m, unsigned long long *__restrict__ scal,
+                                          double *__restrict__ part /* [rows][4][chunk] */) {
+    const int lane = threadIdx.x & 31;
     const double4 *__restrict__ W = t.nodeW;
     // tiles of 128 key-adjacent targets are dealt round-robin in groups of SPH_WALK_DEAL consecutive tiles
-    const int64_t local = (int64_t)blockIdx.x * (GW_WARPS * 32) + threadIdx.x;
-    const int64_t gtile = ((int64_t)(blockIdx.x / SPH_WALK_DEAL) * nranks + rank) * SPH_WALK_DEAL + blockIdx.x % SPH_WALK_DEAL;
+    const int64_t local = (int64_t)bx * (GW_WARPS * 32) + threadIdx.x;
+    const int64_t gtile = ((int64_t)(bx / SPH_WALK_DEAL) * nranks + rank) * SPH_WALK_DEAL + bx % SPH_WALK_DEAL;
     const int64_t s = gtile * (GW_WARPS * 32) + threadIdx.x;
     const bool active = s < N;
     double px = 0, py = 0, pz = 0, hi = 1.0;
@@ -143,7 +138,6 @@ __global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : 8) walk_kernel(int64
     // of tiles); the partial sums are added in row order by walk_reduce_kernel, so results stay deterministic.
     const int2 R = unpack_i2(W[1].z);
     const int rnch = R.y & 0xff;
-    const int row = blockIdx.y, rows = gridDim.y;
     if (row >= rnch) return;
     if (amask) {
         const int near = walk_root_near(W, R, gtile * (GW_WARPS * 32));
@@ -244,6 +238,31 @@ __global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : 8) walk_kernel(int64
     }
 }
 
+// The regular variants launch one block per work item.  The DEEP variants are launched after every regular walk but
+// have work only when it overflowed: a small persistent grid loops over the work items, so that the usual case costs a
+// few hundred blocks that leave at once instead of one empty block per work item (36 us at N = 1e6).
+template <bool COUNT, bool DEEP>
+__global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : 8) walk_kernel(int64_t N, int nranks, int rank, int64_t chunk,
+                                                                 const double4 *__restrict__ pos4,
+                                                                 const double *__restrict__ hs, SphTree t,
+                                                                 double theta_sq, double m,
+                                                                 unsigned long long *__restrict__ scal,
+                                                                 double *__restrict__ part /* [rows][4][chunk] */,
+                                                                 int nbx, int rows) {
+    constexpr int STACK = DEEP ? GW_STACK_DEEP : GW_STACK;
+    __shared__ int4 s_stack[GW_WARPS][STACK];   // {first child, nch | leafmask << 8, lane mask, -}
+    if (walk_skipped<DEEP>(scal)) return;
+    int4 *stack = s_stack[threadIdx.x >> 5];
+    if (!DEEP) {
+        walk_tile<COUNT, DEEP, STACK>(blockIdx.x, blockIdx.y, rows, stack, N, nranks, rank, chunk, pos4, hs, t, theta_sq, m, scal, part);
+    } else {
+        for (int w = blockIdx.x; w < nbx * rows; w += gridDim.x) {
+            walk_tile<COUNT, DEEP, STACK>(w % nbx, w / nbx, rows, stack, N, nranks, rank, chunk, pos4, hs, t, theta_sq, m, scal, part);
+            __syncwarp();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Walk with a pair queue for the sparse part (default; SPH_B200_WALK_DFS=1 selects walk_kernel above).
 //
@@ -328,22 +347,17 @@ __device__ __forceinline__ void leaf_pair(double d_sq, double hi, double hj, dou
     }
 }
 
-template <bool COUNT, bool DEEP>
-__global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : WALK_MINB) walk_pairs_kernel(int64_t N, int nranks, int rank, int64_t chunk,
-                                                                       const double4 *__restrict__ pos4,
-                                                                       const double *__restrict__ hs, SphTree t,
-                                                                       double theta_sq, double th_lo, double th_hi, double m,
-                                                                       int sparse_t, unsigned long long *__restrict__ scal,
-                                                                       double *__restrict__ part /* [8][4][chunk] */) {
-    constexpr int STACK = DEEP ? GP_DEEP : GP_STACK, QCAP = GP_SOFT + (DEEP ? GP_DEEP : GP_SLACK);
-    __shared__ GpWarp<STACK, QCAP - GP_SOFT> s_w[GW_WARPS];
-    if (walk_skipped<DEEP>(scal)) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+template <bool COUNT, bool DEEP, int STACK, int QCAP>
+__device__ __forceinline__ void walk_pairs_tile(int bx, int row, int rows, GpWarp<STACK, QCAP - GP_SOFT> &sm, int64_t N, int nranks,
+                                                int rank, int64_t chunk, const double4 *__restrict__ pos4,
+                                                const double *__restrict__ hs, const SphTree &t, double theta_sq, double th_lo,
+                                                double th_hi, double m, int sparse_t, unsigned long long *__restrict__ scal,
+                                                double *__restrict__ part /* [rows][4][chunk] */) {
+    const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    GpWarp<STACK, QCAP - GP_SOFT> &sm = s_w[warp];
     const double4 *__restrict__ W = t.nodeW;
-    const int64_t local = (int64_t)blockIdx.x * (GW_WARPS * 32) + threadIdx.x;
-    const int64_t gtile = ((int64_t)(blockIdx.x / SPH_WALK_DEAL) * nranks + rank) * SPH_WALK_DEAL + blockIdx.x % SPH_WALK_DEAL;
+    const int64_t local = (int64_t)bx * (GW_WARPS * 32) + threadIdx.x;
+    const int64_t gtile = ((int64_t)(bx / SPH_WALK_DEAL) * nranks + rank) * SPH_WALK_DEAL + bx % SPH_WALK_DEAL;
     const int64_t s = gtile * (GW_WARPS * 32) + threadIdx.x;
     const bool active = s < N;
     double px = 0, py = 0, pz = 0, hi = 1.0;
@@ -360,7 +374,6 @@ __global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : WALK_MINB) walk_pair
     // the root is opened unconditionally (:246-249); its children are dealt to the block rows (see walk_kernel)
     const int2 R = unpack_i2(W[1].z);
     const int rnch = R.y & 0xff;
-    const int row = blockIdx.y, rows = gridDim.y;
     if (row >= rnch) return;
     sm.acc[lane] = make_double4(0.0, 0.0, 0.0, 0.0);
     int sp = 0, qn = 0;
@@ -530,6 +543,30 @@ __global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : WALK_MINB) walk_pair
     }
 }
 
+template <bool COUNT, bool DEEP>
+__global__ void __launch_bounds__(GW_WARPS * 32, DEEP ? 4 : WALK_MINB) walk_pairs_kernel(int64_t N, int nranks, int rank, int64_t chunk,
+                                                                       const double4 *__restrict__ pos4,
+                                                                       const double *__restrict__ hs, SphTree t,
+                                                                       double theta_sq, double th_lo, double th_hi, double m,
+                                                                       int sparse_t, unsigned long long *__restrict__ scal,
+                                                                       double *__restrict__ part /* [rows][4][chunk] */,
+                                                                       int nbx, int rows) {
+    constexpr int STACK = DEEP ? GP_DEEP : GP_STACK, QCAP = GP_SOFT + (DEEP ? GP_DEEP : GP_SLACK);
+    __shared__ GpWarp<STACK, QCAP - GP_SOFT> s_w[GW_WARPS];
+    if (walk_skipped<DEEP>(scal)) return;
+    GpWarp<STACK, QCAP - GP_SOFT> &sm = s_w[threadIdx.x >> 5];
+    if (!DEEP) {
+        walk_pairs_tile<COUNT, DEEP, STACK, QCAP>(blockIdx.x, blockIdx.y, rows, sm, N, nranks, rank, chunk, pos4, hs, t, theta_sq, th_lo,
+                                                  th_hi, m, sparse_t, scal, part);
+    } else {   // see walk_kernel
+        for (int w = blockIdx.x; w < nbx * rows; w += gridDim.x) {
+            walk_pairs_tile<COUNT, DEEP, STACK, QCAP>(w % nbx, w / nbx, rows, sm, N, nranks, rank, chunk, pos4, hs, t, theta_sq, th_lo,
+                                                      th_hi, m, sparse_t, scal, part);
+            __syncwarp();
+        }
+    }
+}
+
 // SPH_B200_WALK_FORCE_DEEP=1 (tests): pretend the regular walk overflowed, so that the DEEP variant produces the result
 __global__ void walk_force_overflow_kernel(unsigned long long *__restrict__ scal) {
     if (scal[SC_ERR] == 0ull) scal[SC_ERR] = (unsigned long long)ERRF_STACK;
@@ -609,24 +646,26 @@ cudaError_t sph_launch_walk(sph_handle *h) {
     const double lo = th2 * (1.0 - 1e-15), hi = th2 * (1.0 + 1e-15);
     const int64_t N = h->N;
     const bool shared = shared_only || h->tree.cap >= (1ll << 27) || h->N >= (1ll << 31);   // node ids that do not fit the pair encoding
-#define WALK_LAUNCH(DEEP)                                                                                                       \
+    const int nbx = (int)blocks;
+    const dim3 grid_deep(148 * 4);       // persistent: loops over the nbx x rows work items when it has to run
+#define WALK_LAUNCH(DEEP, GRID)                                                                                                 \
     do {                                                                                                                        \
         if (shared) {                                                                                                           \
-            if (count) walk_kernel<true, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, h->p.m, h->scal, part);   \
-            else walk_kernel<false, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, h->p.m, h->scal, part);        \
+            if (count) walk_kernel<true, DEEP><<<GRID, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, h->p.m, h->scal, part, nbx, rows);   \
+            else walk_kernel<false, DEEP><<<GRID, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, h->p.m, h->scal, part, nbx, rows);        \
         } else {                                                                                                                \
-            if (count) walk_pairs_kernel<true, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, lo, hi, h->p.m, sparse_t, h->scal, part);   \
-            else walk_pairs_kernel<false, DEEP><<<grid, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, lo, hi, h->p.m, sparse_t, h->scal, part);        \
+            if (count) walk_pairs_kernel<true, DEEP><<<GRID, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, lo, hi, h->p.m, sparse_t, h->scal, part, nbx, rows);   \
+            else walk_pairs_kernel<false, DEEP><<<GRID, GW_WARPS * 32, 0, h->stream>>>(N, h->nranks, h->rank, h->walk_chunk, h->pos4, h->hs, h->tree, th2, lo, hi, h->p.m, sparse_t, h->scal, part, nbx, rows);        \
         }                                                                                                                       \
     } while (0)
-    WALK_LAUNCH(false);
+    WALK_LAUNCH(false, grid);
     cudaEventRecord(h->wev[1], h->stream);
     // trees deeper than 21 levels may overflow the regular variant's stack: the DEEP variant (a no-op otherwise: its
     // blocks leave at once) then redoes every tile with stacks sized for 42 levels
     sph_note(2);
     static const bool force_deep = getenv("SPH_B200_WALK_FORCE_DEEP") != nullptr;
     if (force_deep) walk_force_overflow_kernel<<<1, 1, 0, h->stream>>>(h->scal);
-    WALK_LAUNCH(true);
+    WALK_LAUNCH(true, grid_deep);
 #undef WALK_LAUNCH
     walk_clear_overflow_kernel<<<1, 1, 0, h->stream>>>(h->scal);
     if (rows > 1) {

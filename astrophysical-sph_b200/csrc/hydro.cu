@@ -30,6 +30,14 @@
 namespace {
 
 constexpr int HB = 128;
+// build-time experiments (tools/build_variants.sh): L1 prefetch distance of the gathers (0 = off), resident blocks of the force pass
+#ifndef SPH_PREFETCH
+#define SPH_PREFETCH 0
+#endif
+#ifndef FORCE_MINB
+#define FORCE_MINB 4
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 constexpr double PI_D = 3.141592653589793;
 constexpr double INV_PI_D = 0.3183098861837907;
 
@@ -197,6 +205,7 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int 
     unsigned long long defer = 0ull;     // bit j: the j-th neighbour's list does not hold s (told after the loop)
     for (int j = 0; j < K; ++j) {
         const int nj = lst[j * lstride];
+        if (SPH_PREFETCH > 0 && !TILE && j + SPH_PREFETCH < K) prefetch_l1(pos4 + lst[(j + SPH_PREFETCH) * lstride]);
         double4 pj;
         if (TILE) {
             const unsigned loc = (unsigned)(nj - (int)w0);
@@ -394,7 +403,7 @@ __device__ __forceinline__ void pair_terms(const Target &t, const double4 &pj, c
 }
 
 template <bool POLY, bool TILE>
-__global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int64_t NL, int64_t NS, int K, int64_t t0, int64_t t1,
+__global__ void __launch_bounds__(HB, TILE ? 3 : FORCE_MINB) force_kernel(int64_t N, int64_t NL, int64_t NS, int K, int64_t t0, int64_t t1,
                                                     const double4 *__restrict__ pos4, const double4 *__restrict__ vel4,
                                                     const double4 *__restrict__ pc, const int *__restrict__ nbr,
                                                     const int *__restrict__ perm, const int *__restrict__ kid,
@@ -457,6 +466,10 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : 4) force_kernel(int64_t N, int6
     double mmax = 0.0;
     for (int j = 0; j < K; ++j) {
         const int nj = lst[j * lstride];
+        if (SPH_PREFETCH > 0 && !TILE && j + SPH_PREFETCH < K) {
+            const int np = lst[(j + SPH_PREFETCH) * lstride];
+            prefetch_l1(pos4 + np); prefetch_l1(vel4 + np); prefetch_l1(pc + np);
+        }
         if (nj == (int)s) continue;      // lists arrive unordered from the grouped search: self is recognised by index
         double4 pj, vj, cj;
         if (TILE) {
