@@ -136,22 +136,31 @@ constexpr int TWIN = HB + 2 * TW;       // records in the window
 
 // EOS closure of one particle: isothermal P = cs^2 rho (F/isothermal_hydroKDTree.jl:190), c = cs; polytropic
 // P = K rho^gamma (F/polytrope_hydroKDTree.jl:216), c_i = sqrt(gamma K rho^(gamma-1)) (:186).
-// hr = {h, rho}; pc = {rho, P/rho^2, h, c}: the 32-byte record the force pass gathers per neighbour next to pos4 and vel4.
-// (Measured and dropped: ONE 128-byte record {pos | vel | pc | pad} per particle, i.e. one cache line per gathered
-// neighbour instead of three sectors in three lines - force 0.73 -> 1.08 ms at N = 1e6: a line of a 32-byte array holds
-// four key-adjacent particles, which are mostly neighbours too, so the three arrays use L1 far better.)
-__device__ __forceinline__ void eos_store(int64_t s, double h, double rho, double Kent, int poly, double cs, double gamma,
-                                          double2 *__restrict__ hr, double4 *__restrict__ pc) {
+// Writes hr = {h, rho} and the records the force pass gathers per neighbour: fa = {x, y, z, h}, fb = {vx, vy, vz, rho},
+// fc = {P/rho^2, c}.  The isothermal force needs only fa and fb (P/rho^2 = cs^2 / rho, c = cs): two 32-byte sectors per
+// neighbour instead of three.
+// (Measured and dropped: ONE 128-byte record per particle, i.e. one cache line per gathered neighbour instead of
+// sectors in three lines - force 0.73 -> 1.08 ms at N = 1e6: a line of a 32-byte array holds four key-adjacent
+// particles, which are mostly neighbours too, so separate arrays use L1 far better.)
+struct ForceRecs {
+    double4 *fa, *fb;
+    double2 *fc;
+};
+__device__ __forceinline__ void eos_store(int64_t s, const double4 &pi, const double4 &vi, double h, double rho, int poly,
+                                          double cs, double gamma, double2 *__restrict__ hr, const ForceRecs &f) {
     double P, c;
     if (!poly) {
         P = cs * cs * rho;
         c = cs;
     } else {
+        const double Kent = vi.w;
         c = sqrt(gamma * Kent * pow(rho, gamma - 1));
         P = Kent * pow(rho, gamma);
     }
     hr[s] = make_double2(h, rho);
-    pc[s] = make_double4(rho, P / (rho * rho), h, c);
+    f.fa[s] = make_double4(pi.x, pi.y, pi.z, h);
+    f.fb[s] = make_double4(vi.x, vi.y, vi.z, rho);
+    f.fc[s] = make_double2(P / (rho * rho), c);
 }
 
 // EOS: with one rank the density pass closes the EOS of its target on the spot (every particle is a target);
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int 
                                                       double m, int poly, unsigned long long *__restrict__ scal,
                                                       ExtrasOut x, double *__restrict__ rho_out,
                                                       const double4 *__restrict__ vel4, double cs, double gamma,
-                                                      double2 *__restrict__ hr, double4 *__restrict__ pc) {
+                                                      double2 *__restrict__ hr, ForceRecs frec) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     if (SPH_ERR_BLOCKING(scal) != 0ull) return;
     const int64_t s0 = t0 + (int64_t)blockIdx.x * HB;
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(HB) density_kernel(int64_t N, int64_t NL, int 
         defer &= defer - 1ull;
         push_extra(x, lst[j * lstride], (int)s, scal);
     }
-    if (EOS) eos_store(s, h, m * sum, poly ? vel4[s].w : 0.0, poly, cs, gamma, hr, pc);
+    if (EOS) eos_store(s, pi, vel4[s], h, m * sum, poly, cs, gamma, hr, frec);
     else rho_out[s] = m * sum;
 }
 
@@ -326,12 +335,13 @@ __global__ void __launch_bounds__(HB) extras_sort_kernel(int64_t NL, int64_t t0,
 __global__ void __launch_bounds__(HB) eos_kernel(int64_t N, const double *__restrict__ rho_s, const double4 *__restrict__ pos4,
                                                   const double4 *__restrict__ vel4, int poly, double cs, double gamma,
                                                   const unsigned long long *__restrict__ scal, double2 *__restrict__ hr,
-                                                  double4 *__restrict__ pc) {
+                                                  ForceRecs frec) {
     if (SPH_ERR_BLOCKING(scal) != 0ull) return;
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
-    const double h = sqrt(pos4[s].w) / 2;            // h = r[:, end] ./ 2   (:151)
-    eos_store(s, h, rho_s[s], poly ? vel4[s].w : 0.0, poly, cs, gamma, hr, pc);
+    const double4 pi = pos4[s];
+    const double h = sqrt(pi.w) / 2;                 // h = r[:, end] ./ 2   (:151)
+    eos_store(s, pi, vel4[s], h, rho_s[s], poly, cs, gamma, hr, frec);
 }
 
 // pos4.w = d2k for ALL particles (after the d2k all-gather in multi-GPU runs): the density and force passes read the
@@ -357,17 +367,18 @@ struct Target {
     double x, y, z, h, vx, vy, vz, rho, prr, cs, hinv, ct4;
 };
 
+// A = {x, y, z, h} and B = {vx, vy, vz, rho} of the partner, prr_j = P_j / rho_j^2, cs_j its sound speed
 template <bool POLY, bool FWD>
-__device__ __forceinline__ void pair_terms(const Target &t, const double4 &pj, const double4 &vj, const double4 &cj, bool rev,
+__device__ __forceinline__ void pair_terms(const Target &t, const double4 &A, const double4 &B, double prr_j, double cs_j, bool rev,
                                            double m, double alpha, double beta, double &ax, double &ay, double &az,
                                            double &dk, double &svdw, double &mmax) {
-    const double dx = t.x - pj.x, dy = t.y - pj.y, dz = t.z - pj.z;           // getTreeDiffs: f_i - f_j (:93)
+    const double dx = t.x - A.x, dy = t.y - A.y, dz = t.z - A.z;              // getTreeDiffs: f_i - f_j (:93)
     const double d2 = sph_d2_exact(dx, dy, dz);
     const double rinv = d2 > 0.0 ? fast_rsqrt(d2) : 0.0;
     const double r = d2 * rinv;
-    const double h_avg = (t.h + cj.z) / 2;                                   // getVectorTreeAvgs (:111)
-    const double rho_avg = (t.rho + cj.x) / 2;
-    const double vx = t.vx - vj.x, vy = t.vy - vj.y, vz = t.vz - vj.z;
+    const double h_avg = (t.h + A.w) / 2;                                    // getVectorTreeAvgs (:111)
+    const double rho_avg = (t.rho + B.w) / 2;
+    const double vx = t.vx - B.x, vy = t.vy - B.y, vz = t.vz - B.z;
     const double vdr = (vx * dx + vy * dy) + vz * dz;                        // (:210)
     const double mu = fmin(h_avg * vdr * fast_rcp(d2 + 0.01 * (h_avg * h_avg)), 0.0);   // (:211)
     const double rinv_rho = fast_rcp(rho_avg);
@@ -382,33 +393,56 @@ __device__ __forceinline__ void pair_terms(const Target &t, const double4 &pj, c
         mmax = fmax(mmax, mu);
         double ct;
         if (!POLY) ct = m * (t.prr + Pi / 2);                                // iso :232
-        else ct = m * ((t.prr + cj.y) + Pi) / 2;                             // poly :235
+        else ct = m * ((t.prr + prr_j) + Pi) / 2;                            // poly :235
         coef = ct * dW;
         if (POLY) dk += m * Pi * vdw / 2;                                    // evolve_K! poly :305-311
     }
     if (rev) {
-        const double hinv_j = fast_rcp(cj.z);
+        const double hinv_j = fast_rcp(A.w);
         const double hi2 = hinv_j * hinv_j;
         const double ct4_j = INV_PI_D * (hi2 * hi2);                         // 1 / (pi h_j^4)
         const double q = r * hinv_j;
         const double dW = kernel_dWdr(ct4_j, hinv_j, q, rinv, POLY);
-        const double Pi = ((-alpha) * (POLY ? cj.w : t.cs) * mu + bmu2) * rinv_rho;     // c = c_j (the list owner's)
+        const double Pi = ((-alpha) * (POLY ? cs_j : t.cs) * mu + bmu2) * rinv_rho;     // c = c_j (the list owner's)
         double ct;
-        if (!POLY) ct = m * (cj.y + Pi / 2);
-        else ct = m * ((cj.y + t.prr) + Pi) / 2;
+        if (!POLY) ct = m * (prr_j + Pi / 2);
+        else ct = m * ((prr_j + t.prr) + Pi) / 2;
         coef += ct * dW;
         if (POLY) dk += m * Pi * (dW * vdr) / 2;
     }
     ax -= coef * dx; ay -= coef * dy; az -= coef * dz;
 }
 
+// P/rho^2 and c of a partner: polytropic - the fc record; isothermal - cs^2 / rho_j and cs (no third gather)
+template <bool POLY>
+__device__ __forceinline__ void partner_eos(const double2 *__restrict__ fc, int64_t j, double rho_j, double cs2, double cs,
+                                            double &prr_j, double &cs_j) {
+    if (POLY) {
+        const double2 c = fc[j];
+        prr_j = c.x; cs_j = c.y;
+    } else {
+        prr_j = cs2 * fast_rcp(rho_j);
+        cs_j = cs;
+    }
+}
+
+// "s in N(j)" from j's smoothing length when the distance is clearly inside / outside (2 h_j)^2 = d2k_j, else exactly
+__device__ __forceinline__ bool in_list_fast(double d2, double h_j, int a, int b, const double *__restrict__ d2k,
+                                             const int *__restrict__ perm, const int *__restrict__ kid) {
+    const double t4 = 4.0 * (h_j * h_j);
+    if (d2 < t4 * (1.0 - 1e-13)) return true;
+    if (d2 > t4 * (1.0 + 1e-13)) return false;
+    return in_list_of(d2, d2k[b], a, b, perm, kid);
+}
+
 template <bool POLY, bool TILE>
 __global__ void __launch_bounds__(HB, TILE ? 3 : FORCE_MINB) force_kernel(int64_t N, int64_t NL, int64_t NS, int K, int64_t t0, int64_t t1,
-                                                    const double4 *__restrict__ pos4, const double4 *__restrict__ vel4,
-                                                    const double4 *__restrict__ pc, const int *__restrict__ nbr,
+                                                    const double4 *__restrict__ fa, const double4 *__restrict__ fb,
+                                                    const double2 *__restrict__ fc, const double *__restrict__ d2k,
+                                                    const int *__restrict__ nbr,
                                                     const int *__restrict__ perm, const int *__restrict__ kid,
                                                     const int *__restrict__ ecnt, const int *__restrict__ ext, int ecap,
-                                                    double m, double alpha, double beta,
+                                                    double m, double alpha, double beta, double cs2,
                                                     const unsigned long long *__restrict__ scal,
                                                     double *__restrict__ ahyd, double *__restrict__ dkdt,
                                                     double *__restrict__ sumvdw, double *__restrict__ mumax) {
@@ -418,14 +452,16 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : FORCE_MINB) force_kernel(int64_
     const int64_t s = s0 + threadIdx.x;
     const int *lst = nbr + s;
     int64_t lstride = NL;
-    const double4 *wpos = nullptr, *wvel = nullptr, *wpc = nullptr;
+    const double4 *wa = nullptr, *wb = nullptr;
+    const double2 *wc = nullptr;
     int64_t w0 = 0;
     int wn = 0;
     if (TILE) {
         unsigned long long *bar = reinterpret_cast<unsigned long long *>(dyn_smem);
-        double4 *s_pos = reinterpret_cast<double4 *>(dyn_smem + 128);
-        double4 *s_vel = s_pos + TWIN, *s_pc = s_vel + TWIN;
-        int *s_idx = reinterpret_cast<int *>(s_pc + TWIN);
+        double4 *s_a = reinterpret_cast<double4 *>(dyn_smem + 128);
+        double4 *s_b = s_a + TWIN;
+        double2 *s_c = reinterpret_cast<double2 *>(s_b + TWIN);
+        int *s_idx = reinterpret_cast<int *>(s_c + TWIN);
         w0 = s0 - TW < 0 ? 0 : s0 - TW;
         const int64_t w1 = s0 + HB + TW > N ? N : s0 + HB + TW;
         wn = (int)(w1 - w0);
@@ -435,27 +471,26 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : FORCE_MINB) force_kernel(int64_
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const unsigned wb = (unsigned)(wn * sizeof(double4));
-            mbar_expect_tx(bar, 3 * wb + (unsigned)((size_t)K * HB * sizeof(int)));
-            bulk_g2s(s_pos, pos4 + w0, wb, bar);
-            bulk_g2s(s_vel, vel4 + w0, wb, bar);
-            bulk_g2s(s_pc, pc + w0, wb, bar);
+            const unsigned wb4 = (unsigned)(wn * sizeof(double4)), wb2 = POLY ? (unsigned)(wn * sizeof(double2)) : 0u;
+            mbar_expect_tx(bar, 2 * wb4 + wb2 + (unsigned)((size_t)K * HB * sizeof(int)));
+            bulk_g2s(s_a, fa + w0, wb4, bar);
+            bulk_g2s(s_b, fb + w0, wb4, bar);
+            if (POLY) bulk_g2s(s_c, fc + w0, wb2, bar);
             for (int j = 0; j < K; ++j) bulk_g2s(s_idx + j * HB, nbr + (int64_t)j * NL + s0, HB * sizeof(int), bar);
         }
         mbar_wait(bar, 0);
         lst = s_idx + threadIdx.x;
         lstride = HB;
-        wpos = s_pos; wvel = s_vel; wpc = s_pc;
+        wa = s_a; wb = s_b; wc = s_c;
     }
     if (s >= t1) return;
     Target t;
     {
-        const double4 pi = TILE ? wpos[s - w0] : pos4[s];
-        const double4 vi = TILE ? wvel[s - w0] : vel4[s];
-        const double4 ci = TILE ? wpc[s - w0] : pc[s];
-        t.x = pi.x; t.y = pi.y; t.z = pi.z; t.h = ci.z;
-        t.vx = vi.x; t.vy = vi.y; t.vz = vi.z;
-        t.rho = ci.x; t.prr = ci.y; t.cs = ci.w;
+        const double4 pi = fa[s], vi = fb[s];
+        const double2 ci = fc[s];
+        t.x = pi.x; t.y = pi.y; t.z = pi.z; t.h = pi.w;
+        t.vx = vi.x; t.vy = vi.y; t.vz = vi.z; t.rho = vi.w;
+        t.prr = ci.x; t.cs = ci.y;
         const double h2 = t.h * t.h;
         t.ct4 = 1 / (PI_D * (h2 * h2));
         t.hinv = 1 / t.h;
@@ -468,24 +503,22 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : FORCE_MINB) force_kernel(int64_
         const int nj = lst[j * lstride];
         if (SPH_PREFETCH > 0 && !TILE && j + SPH_PREFETCH < K) {
             const int np = lst[(j + SPH_PREFETCH) * lstride];
-            prefetch_l1(pos4 + np); prefetch_l1(vel4 + np); prefetch_l1(pc + np);
+            prefetch_l1(fa + np); prefetch_l1(fb + np);
         }
         if (nj == (int)s) continue;      // lists arrive unordered from the grouped search: self is recognised by index
-        double4 pj, vj, cj;
+        const double4 *pa = fa + nj, *pb = fb + nj;
+        const double2 *pcj = fc + nj;
         if (TILE) {
             const unsigned loc = (unsigned)(nj - (int)w0);
-            const bool in = loc < (unsigned)wn;
-            const double4 *pp = in ? wpos + loc : pos4 + nj;
-            const double4 *vp = in ? wvel + loc : vel4 + nj;
-            const double4 *cp = in ? wpc + loc : pc + nj;
-            pj = *pp; vj = *vp; cj = *cp;
-        } else {
-            pj = pos4[nj]; vj = vel4[nj]; cj = pc[nj];
+            if (loc < (unsigned)wn) { pa = wa + loc; pb = wb + loc; pcj = wc + loc; }      // generic loads: window or global
         }
+        const double4 A = *pa, B = *pb;
+        double prr_j, cs_j;
+        partner_eos<POLY>(pcj, 0, B.w, cs2, t.cs, prr_j, cs_j);
         // does nj's list contain s?  then its reaction on s is gathered here (mutual pair)
-        const double d2 = sph_d2_exact(t.x - pj.x, t.y - pj.y, t.z - pj.z);
-        const bool rev = in_list_of(d2, pj.w, (int)s, nj, perm, kid);
-        pair_terms<POLY, true>(t, pj, vj, cj, rev, m, alpha, beta, ax, ay, az, dk, svdw, mmax);
+        const double d2 = sph_d2_exact(t.x - A.x, t.y - A.y, t.z - A.z);
+        const bool rev = in_list_fast(d2, A.w, (int)s, nj, d2k, perm, kid);
+        pair_terms<POLY, true>(t, A, B, prr_j, cs_j, rev, m, alpha, beta, ax, ay, az, dk, svdw, mmax);
     }
     // reverse partners outside the own list (3.7 on average), ascending index (extras_sort_kernel)
     int ne = ecnt[s];
@@ -493,8 +526,10 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : FORCE_MINB) force_kernel(int64_
     double dummy_s = 0.0, dummy_m = 0.0;
     for (int e = 0; e < ne; ++e) {
         const int k = ext[(int64_t)e * NL + s];
-        const double4 pj = pos4[k], vj = vel4[k], cj = pc[k];
-        pair_terms<POLY, false>(t, pj, vj, cj, true, m, alpha, beta, ax, ay, az, dk, dummy_s, dummy_m);
+        const double4 A = fa[k], B = fb[k];
+        double prr_j, cs_j;
+        partner_eos<POLY>(fc, k, B.w, cs2, t.cs, prr_j, cs_j);
+        pair_terms<POLY, false>(t, A, B, prr_j, cs_j, true, m, alpha, beta, ax, ay, az, dk, dummy_s, dummy_m);
     }
     ahyd[s] = ax; ahyd[s + NS] = ay; ahyd[s + 2 * NS] = az;
     if (POLY) dkdt[s] = dk;
@@ -506,10 +541,11 @@ __global__ void __launch_bounds__(HB, TILE ? 3 : FORCE_MINB) force_kernel(int64_
 // Each such particle scans the list for its entries and adds them in ascending index order (rare, deterministic).
 template <bool POLY>
 __global__ void __launch_bounds__(HB) force_overflow_kernel(int64_t NS, int64_t t0, int64_t t1,
-                                                             const double4 *__restrict__ pos4, const double4 *__restrict__ vel4,
-                                                             const double4 *__restrict__ pc, const int *__restrict__ ecnt,
+                                                             const double4 *__restrict__ fa, const double4 *__restrict__ fb,
+                                                             const double2 *__restrict__ fc, const int *__restrict__ ecnt,
                                                              int ecap, const int2 *__restrict__ ovf, int ovcap, double m,
-                                                             double alpha, double beta, const unsigned long long *__restrict__ scal,
+                                                             double alpha, double beta, double cs2,
+                                                             const unsigned long long *__restrict__ scal,
                                                              double *__restrict__ ahyd, double *__restrict__ dkdt) {
     if (SPH_ERR_BLOCKING(scal) != 0ull) return;
     const unsigned long long no = scal[SC_OVF];
@@ -519,10 +555,11 @@ __global__ void __launch_bounds__(HB) force_overflow_kernel(int64_t NS, int64_t 
     if (s >= t1 || ecnt[s] <= ecap) return;
     Target t;
     {
-        const double4 pi = pos4[s], vi = vel4[s], ci = pc[s];
-        t.x = pi.x; t.y = pi.y; t.z = pi.z; t.h = ci.z;
-        t.vx = vi.x; t.vy = vi.y; t.vz = vi.z;
-        t.rho = ci.x; t.prr = ci.y; t.cs = ci.w;
+        const double4 pi = fa[s], vi = fb[s];
+        const double2 ci = fc[s];
+        t.x = pi.x; t.y = pi.y; t.z = pi.z; t.h = pi.w;
+        t.vx = vi.x; t.vy = vi.y; t.vz = vi.z; t.rho = vi.w;
+        t.prr = ci.x; t.cs = ci.y;
         t.ct4 = 0.0; t.hinv = 0.0;
     }
     double ax = 0.0, ay = 0.0, az = 0.0, dk = 0.0, d0 = 0.0, d1 = 0.0;
@@ -534,8 +571,10 @@ __global__ void __launch_bounds__(HB) force_overflow_kernel(int64_t NS, int64_t 
             if (p.x == (int)s && p.y > last && p.y < best) best = p.y;
         }
         if (best == 0x7fffffff) break;
-        const double4 pj = pos4[best], vj = vel4[best], cj = pc[best];
-        pair_terms<POLY, false>(t, pj, vj, cj, true, m, alpha, beta, ax, ay, az, dk, d0, d1);
+        const double4 A = fa[best], B = fb[best];
+        double prr_j, cs_j;
+        partner_eos<POLY>(fc, best, B.w, cs2, t.cs, prr_j, cs_j);
+        pair_terms<POLY, false>(t, A, B, prr_j, cs_j, true, m, alpha, beta, ax, ay, az, dk, d0, d1);
         last = best;
     }
     ahyd[s] += ax; ahyd[s + NS] += ay; ahyd[s + 2 * NS] += az;
@@ -551,7 +590,7 @@ inline ExtrasOut extras_of(sph_handle *h, int64_t t0, int64_t t1) {
 }
 
 constexpr size_t DENS_SMEM = 128 + sizeof(double4) * TWIN;          // + K * HB * 4
-constexpr size_t FORCE_SMEM = 128 + 3 * sizeof(double4) * TWIN;     // + K * HB * 4
+constexpr size_t FORCE_SMEM = 128 + (2 * sizeof(double4) + sizeof(double2)) * TWIN;     // + K * HB * 4
 
 }  // namespace
 
@@ -587,16 +626,16 @@ static cudaError_t launch_density(sph_handle *h, int64_t t0, int64_t t1) {
         }
         density_kernel<true, EOS><<<blocks, HB, smem, h->stream>>>(h->N, h->NL, h->K, t0, t1, h->pos4, h->nbr, h->perm, h->kid,
                                                                    h->p.m, poly, h->scal, x, h->rho_s, h->vel4, h->p.cs, h->p.gamma,
-                                                                   h->hr, h->pc);
+                                                                   h->hr, ForceRecs{h->fa, h->fb, h->fc});
     } else {
         density_kernel<false, EOS><<<blocks, HB, 0, h->stream>>>(h->N, h->NL, h->K, t0, t1, h->pos4, h->nbr, h->perm, h->kid,
                                                                  h->p.m, poly, h->scal, x, h->rho_s, h->vel4, h->p.cs, h->p.gamma,
-                                                                 h->hr, h->pc);
+                                                                 h->hr, ForceRecs{h->fa, h->fb, h->fc});
     }
     return cudaGetLastError();
 }
 
-// with_eos: one rank - the EOS of every target is closed in the same kernel (hr, pc written); several ranks - only
+// with_eos: one rank - the EOS of every target is closed in the same kernel (hr and the force records written); several ranks - only
 // rho_s of the owned targets, sph_launch_eos follows the all-gather
 cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1, bool with_eos) {
     if (t1 <= t0) return cudaSuccess;
@@ -626,7 +665,7 @@ cudaError_t sph_launch_extras_sort(sph_handle *h, int64_t t0, int64_t t1) {
 cudaError_t sph_launch_eos(sph_handle *h) {
     sph_note(1);
     eos_kernel<<<(int)((h->N + HB - 1) / HB), HB, 0, h->stream>>>(h->N, h->rho_s, h->pos4, h->vel4, h->p.eos == SPH_EOS_POLYTROPIC,
-                                                                  h->p.cs, h->p.gamma, h->scal, h->hr, h->pc);
+                                                                  h->p.cs, h->p.gamma, h->scal, h->hr, ForceRecs{h->fa, h->fb, h->fc});
     return cudaGetLastError();
 }
 
@@ -634,6 +673,7 @@ template <bool POLY>
 static cudaError_t launch_force(sph_handle *h, int64_t t0, int64_t t1) {
     const int64_t nt = t1 - t0;
     const int blocks = (int)((nt + HB - 1) / HB);
+    const double cs2 = h->p.cs * h->p.cs;
     if (use_tile_kernels() && (t0 % HB) == 0) {
         const size_t smem = FORCE_SMEM + (size_t)h->K * HB * sizeof(int);
         static bool attr = false;
@@ -642,16 +682,16 @@ static cudaError_t launch_force(sph_handle *h, int64_t t0, int64_t t1) {
             if (e != cudaSuccess) return e;
             attr = true;
         }
-        force_kernel<POLY, true><<<blocks, HB, smem, h->stream>>>(h->N, h->NL, h->NS, h->K, t0, t1, h->pos4, h->vel4, h->pc, h->nbr,
+        force_kernel<POLY, true><<<blocks, HB, smem, h->stream>>>(h->N, h->NL, h->NS, h->K, t0, t1, h->fa, h->fb, h->fc, h->d2k, h->nbr,
                                                                   h->perm, h->kid, h->ecnt, h->ext, h->ecap, h->p.m, h->p.alpha,
-                                                                  h->p.beta, h->scal, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax);
+                                                                  h->p.beta, cs2, h->scal, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax);
     } else {
-        force_kernel<POLY, false><<<blocks, HB, 0, h->stream>>>(h->N, h->NL, h->NS, h->K, t0, t1, h->pos4, h->vel4, h->pc, h->nbr,
+        force_kernel<POLY, false><<<blocks, HB, 0, h->stream>>>(h->N, h->NL, h->NS, h->K, t0, t1, h->fa, h->fb, h->fc, h->d2k, h->nbr,
                                                                 h->perm, h->kid, h->ecnt, h->ext, h->ecap, h->p.m, h->p.alpha,
-                                                                h->p.beta, h->scal, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax);
+                                                                h->p.beta, cs2, h->scal, h->s_ahyd, h->s_dkdt, h->s_sumvdw, h->s_mumax);
     }
-    force_overflow_kernel<POLY><<<blocks, HB, 0, h->stream>>>(h->NS, t0, t1, h->pos4, h->vel4, h->pc, h->ecnt, h->ecap, h->ovf,
-                                                              (int)h->ovcap, h->p.m, h->p.alpha, h->p.beta, h->scal, h->s_ahyd,
+    force_overflow_kernel<POLY><<<blocks, HB, 0, h->stream>>>(h->NS, t0, t1, h->fa, h->fb, h->fc, h->ecnt, h->ecap, h->ovf,
+                                                              (int)h->ovcap, h->p.m, h->p.alpha, h->p.beta, cs2, h->scal, h->s_ahyd,
                                                               h->s_dkdt);
     return cudaGetLastError();
 }

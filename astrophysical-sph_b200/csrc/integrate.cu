@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(IB) finish_kernel(int64_t N, int64_t NS, const
 __global__ void __launch_bounds__(IB) unpermute_kernel(int64_t N, int64_t NS, const int *__restrict__ perm,
                                                         const double *__restrict__ s_red, const double *__restrict__ walk_buf,
                                                         int nranks, int64_t wchunk, const double2 *__restrict__ hr,
-                                                        const double4 *__restrict__ pc, double *__restrict__ o_ahyd,
+                                                        const double2 *__restrict__ fc, double *__restrict__ o_ahyd,
                                                         double *__restrict__ o_g, double *__restrict__ o_rho,
                                                         double *__restrict__ o_phi, double *__restrict__ o_sumvdw,
                                                         double *__restrict__ o_mumax, double *__restrict__ o_cs,
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(IB) unpermute_kernel(int64_t N, int64_t NS, co
         o_dkdt[i] = s_red[s + 3 * NS];
         o_sumvdw[i] = s_red[s + 4 * NS];
         o_mumax[i] = s_red[s + 5 * NS];
-        o_cs[i] = pc[s].w;
+        o_cs[i] = fc[s].y;
     }
 }
 
@@ -89,7 +89,7 @@ __global__ void dt_init_kernel(unsigned long long *scal) { scal[SC_DT] = 0x7ff00
 __global__ void __launch_bounds__(IB) dt_kernel(int64_t N, int64_t NS, const double4 *__restrict__ vel4,
                                                  const double *__restrict__ s_red, const double *__restrict__ walk_buf,
                                                  int nranks, int64_t wchunk, const double2 *__restrict__ hr,
-                                                 const double4 *__restrict__ pc, double G, double m, double alpha, double beta,
+                                                 const double2 *__restrict__ fc, double G, double m, double alpha, double beta,
                                                  unsigned long long *__restrict__ scal) {
     double best = __longlong_as_double(0x7ff0000000000000LL);
     bool bad = false;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(IB) dt_kernel(int64_t N, int64_t NS, const dou
         const double vel_r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y)), __dmul_rn(v.z, v.z)));
         const double a_r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az)));
         const double2 hrs = hr[s];
-        const double h = hrs.x, c = pc[s].w;
+        const double h = hrs.x, c = fc[s].y;
         const double abs_div_v = fabs(-(__dmul_rn(m, s_red[s + 4 * NS])) / hrs.y);
         const double c1 = 1 / abs_div_v;
         const double c2 = h / vel_r;
@@ -264,7 +264,7 @@ cudaError_t sph_launch_unpermute(sph_handle *h) {
     if (h->outputs_fresh) return cudaSuccess;
     sph_note(1);
     unpermute_kernel<<<grid_for(h->N), IB, 0, h->stream>>>(h->N, h->NS, h->perm, h->s_red, h->walk_buf, h->nranks, h->walk_chunk,
-                                                            h->hr, h->pc, h->o_ahyd, h->o_g, h->o_rho, h->o_phi, h->o_sumvdw,
+                                                            h->hr, h->fc, h->o_ahyd, h->o_g, h->o_rho, h->o_phi, h->o_sumvdw,
                                                             h->o_mumax, h->o_cs, h->o_dkdt);
     h->outputs_fresh = true;
     return cudaGetLastError();
@@ -274,7 +274,7 @@ cudaError_t sph_launch_dt(sph_handle *h) {
     sph_note(3);
     dt_init_kernel<<<1, 1, 0, h->stream>>>(h->scal);
     dt_kernel<<<RED_BLOCKS, IB, 0, h->stream>>>(h->N, h->NS, h->vel4, h->s_red, h->walk_buf, h->nranks, h->walk_chunk, h->hr,
-                                                 h->pc, h->p.G, h->p.m, h->p.alpha, h->p.beta, h->scal);
+                                                 h->fc, h->p.G, h->p.m, h->p.alpha, h->p.beta, h->scal);
     dt_final_kernel<<<1, 1, 0, h->stream>>>(h->scal, h->stat_dev);
     return cudaGetLastError();
 }

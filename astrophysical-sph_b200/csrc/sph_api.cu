@@ -433,7 +433,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(dalloc(&h->o_mumax, N)); CK(dalloc(&h->o_cs, N)); CK(dalloc(&h->o_dkdt, N)); CK(dalloc(&h->o_ahyd, 3 * N));
     CK(dalloc(&h->o_g, 3 * N));
     CK(dalloc(&h->keys, N)); CK(dalloc(&h->keys_alt, N)); CK(dalloc(&h->klo, N)); CK(dalloc(&h->perm, N)); CK(dalloc(&h->perm_alt, N));
-    CK(dalloc(&h->pos4, NS)); CK(dalloc(&h->vel4, NS)); CK(dalloc(&h->hr, NS)); CK(dalloc(&h->pc, NS));
+    CK(dalloc(&h->pos4, NS)); CK(dalloc(&h->vel4, NS)); CK(dalloc(&h->hr, NS)); CK(dalloc(&h->fa, NS)); CK(dalloc(&h->fb, NS)); CK(dalloc(&h->fc, NS));
     CK(dalloc(&h->rho_s, NS)); CK(dalloc(&h->hs, NS)); CK(dalloc(&h->d2k, NS)); CK(dalloc(&h->kid, NS)); CK(dalloc(&h->nbr, NL * K));
     CK(dalloc(&h->ecnt, NL)); CK(dalloc(&h->ext, NL * (size_t)SPH_ECAP));
     h->ovcap = (int64_t)(N / 4 > 65536 ? N / 4 : 65536);
@@ -502,7 +502,7 @@ int sph_destroy(sph_handle *h) {
     if (h->nccl && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t)h->nccl);
     void *ptrs[] = {h->pos, h->vel, h->kent, h->acc, h->pos_half, h->vel_half, h->in_pos, h->in_vel, h->in_kent,
                     h->in_acc, h->o_rho, h->o_h, h->o_phi, h->o_sumvdw, h->o_mumax, h->o_cs, h->o_dkdt, h->o_ahyd,
-                    h->o_g, h->keys, h->keys_alt, h->klo, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->pc,
+                    h->o_g, h->keys, h->keys_alt, h->klo, h->perm, h->perm_alt, h->sort_tmp, h->pos4, h->vel4, h->hr, h->fa, h->fb, h->fc,
                     h->rho_s, h->hs, h->d2k, h->kid, h->nbr, h->ecnt, h->ext, h->ovf, h->outbox, h->inbox, h->s_red, h->walk_buf, h->walk_part, h->cnt,
                     h->base, h->scal, h->stat_dev, h->red_partial, h->tree.nodeI, h->tree.nodeA, h->tree.nodeB,
                     h->tree.nodeC, h->tree.nodeD, h->tree.nodeW, h->tree.nodeBC, h->tree.parent, h->tree.arrive, h->tree.leaf_of, h->tree.nstart, h->tree.ncount, h->tree.ndepth, h->tree.old_start,

@@ -4,7 +4,8 @@
 // CURRENT evaluation, "orig" = the caller's particle order):
 //   state   pos[3N] vel[3N] kent[N] acc[3N]                      orig, column-major like the Julia matrices
 //   sort    keys[N] u64 (21 levels x 3 bits), perm[N] i32        perm[s] = orig id of sorted slot s
-//   sorted  pos4[N] double4 {x,y,z,d2k = (2h)^2}, vel4[N] double4 {vx,vy,vz,K_i}, hr[N] double2 {h,rho}, pc[N] double4 {rho,P/rho^2,h,c}
+//   sorted  pos4[N] double4 {x,y,z,d2k = (2h)^2}, vel4[N] double4 {vx,vy,vz,K_i}, hr[N] double2 {h,rho},
+//           force records fa[N] double4 {x,y,z,h}, fb[N] double4 {vx,vy,vz,rho}, fc[N] double2 {P/rho^2,c}
 //   tree    BFS-ordered linear octree: nodeI int2 {first child | particle, nchild | leafmask << 8 (0 = leaf)},
 //           nodeA double4 {com, mass}, nodeB double4 {lo.xyz, hi.x}, nodeC double4 {hi.y, hi.z, (2L)^2, L}, nodeD double2 {(2L)^2, max |corner - com|},
 //           nstart/ncount i32 particle range of the node in the sorted arrays
@@ -190,7 +191,8 @@ struct sph_handle {
     // sorted working set
     double4 *pos4 = nullptr, *vel4 = nullptr;
     double2 *hr = nullptr;      // {h, rho}
-    double4 *pc = nullptr;      // {rho, P/rho^2, h, c}: the record the force pass gathers per neighbour
+    double4 *fa = nullptr, *fb = nullptr;   // {x, y, z, h}, {vx, vy, vz, rho}: what the force pass gathers per neighbour
+    double2 *fc = nullptr;                  // {P/rho^2, c} (gathered by the polytropic force only)
     double *rho_s = nullptr;    // density of the owned targets (all-gathered in multi-GPU runs)
     double *hs = nullptr;       // smoothing length of every particle, set right after the search (the walk starts from it)
     double *d2k = nullptr;      // K-th squared distance
@@ -286,7 +288,7 @@ cudaError_t sph_launch_density(sph_handle *h, int64_t t0, int64_t t1, bool with_
 cudaError_t sph_launch_outbox_header(sph_handle *h);
 cudaError_t sph_launch_extras_merge(sph_handle *h, int64_t t0, int64_t t1);
 cudaError_t sph_launch_extras_sort(sph_handle *h, int64_t t0, int64_t t1);     // fixed (ascending) order of every particle's extras
-cudaError_t sph_launch_eos(sph_handle *h);                                 // several ranks: hr, pc of ALL particles
+cudaError_t sph_launch_eos(sph_handle *h);                                 // several ranks: hr and the force records of ALL particles
 cudaError_t sph_launch_force(sph_handle *h, int64_t t0, int64_t t1);
 
 // ---- gravity.cu ----------------------------------------------------------------------------------

@@ -49,7 +49,12 @@ function check(h, rc)
     error("libsph_b200 error $rc: $msg")
 end
 
+const ABI_VERSION = 2      # SPH_B200_ABI_VERSION of include/sph_b200.h this file was written against
+const ERR_NAN = -8         # dt came out NaN: the reference's loop ends here (minimum() propagates NaN, `while t < tEnd` fails)
+
 function create(N::Integer, Kh::Integer, eos::Symbol; m, cs=0.0, gamma=5/3, G, theta, alpha, beta, U=0.0, device=0)
+    v = ccall((:sph_abi_version, LIB), Cint, ())
+    v == ABI_VERSION || error("libsph_b200 ABI version $v, expected $ABI_VERSION")
     p = Ref(Params(N, Kh, eos == :polytropic ? 1 : 0, m, cs, gamma, G, theta, alpha, beta, U, device, 0))
     out = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:sph_create, LIB), Cint, (Ref{Params}, Ref{Ptr{Cvoid}}), p, out)
