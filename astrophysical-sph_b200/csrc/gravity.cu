@@ -376,7 +376,7 @@ __device__ __forceinline__ void walk_pairs_tile(int bx, int row, int rows, GpWar
     const int rnch = R.y & 0xff;
     if (row >= rnch) return;
     sm.acc[lane] = make_double4(0.0, 0.0, 0.0, 0.0);
-    int sp = 0, qn = 0;
+    int sp = 0;
     if (amask) {
         const int near = walk_root_near(W, R, gtile * (GW_WARPS * 32));
         if (lane == 0) {
@@ -390,6 +390,7 @@ __device__ __forceinline__ void walk_pairs_tile(int bx, int row, int rows, GpWar
         sp = __shfl_sync(0xffffffffu, sp, 0);
     }
     __syncwarp();
+    int qn = 0;
     for (;;) {
         if (qn >= 32 || (sp == 0 && qn > 0)) {
             // ---- one round of the pair queue: lane k evaluates pair k of the top B
