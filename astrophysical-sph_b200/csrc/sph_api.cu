@@ -653,10 +653,13 @@ int sph_step(sph_handle *h, int nsteps, sph_step_info *info) {
     }
     double *log_dev = h->log_dev;
     double *graph_row = log_dev + (h->log_cap - 1) * 11;      // the captured step writes its row here
-    // Small problems are bound by launch latency (N = 5 000: ~135 launches of a few microseconds each per step): once the
-    // handle has search hints, ONE step is captured into a CUDA graph and replayed.  Single GPU, N <= SPH_B200_GRAPH_N
-    // (default 262 144; 0 disables).  The phase timers are not recorded during a replay (sph_get_timings then fails).
-    static const int64_t graph_n = getenv("SPH_B200_GRAPH_N") ? atoll(getenv("SPH_B200_GRAPH_N")) : 262144;
+    // Once the handle has search hints, ONE step is captured into a CUDA graph and replayed: small problems are bound by
+    // launch latency (N = 5 000: ~135 launches of a few microseconds each per step, 1.72 -> 1.22 ms), and at N = 1e6 the
+    // replay still saves the gaps between ~180 dependent launches (19.68 -> 19.45 ms per step).  N <= SPH_B200_GRAPH_N
+    // (default: any N; 0 disables).  The phase timers are not recorded during a replay: sph_get_timings then fails
+    // and the caller times one sph_eval_state instead (bench.py does).
+    static const int64_t graph_n = getenv("SPH_B200_GRAPH_N") ? atoll(getenv("SPH_B200_GRAPH_N")) : (int64_t)1 << 40;
+    // (one GPU only: a capture that includes the NCCL calls of the two communicators did not complete on 2 GPUs)
     static const bool trace = getenv("SPH_B200_TRACE") != nullptr;
     int rc = SPH_OK;
     for (int s = 0; s < nsteps && rc == SPH_OK; ++s) {
