@@ -35,6 +35,9 @@ __device__ __forceinline__ int64_t eff_n(int64_t n, const unsigned long long *n_
 // so a tile only ever waits for tiles whose blocks are already running).
 constexpr int OS_ITEMS = 8;
 constexpr int OS_TILE = RS_THREADS * OS_ITEMS;
+#ifndef OS_WIN
+#define OS_WIN 8                 // predecessors read per look-back round trip (build-time experiment: tools/build_variants.sh)
+#endif
 constexpr unsigned OS_AGG = 1u << 30, OS_INC = 2u << 30, OS_MASK = (1u << 30) - 1u;
 
 __global__ void __launch_bounds__(RS_THREADS) os_hist_kernel(const uint64_t *__restrict__ keys, int64_t n_cap,
@@ -120,14 +123,15 @@ __global__ void __launch_bounds__(RS_THREADS) os_pass_kernel(const uint64_t *__r
             status[d] = OS_INC | total;
         } else {
             status[(size_t)tile * RS_BINS + d] = OS_AGG | total;
-            // windows of 8 predecessors: the 8 loads are independent, so one L2 round trip covers 8 tiles
+            // windows of OS_WIN predecessors: the loads of a window are independent, so one L2 round trip covers them
+            // all (most predecessors only hold their local count yet, so a late tile walks back a long way)
             bool done = false;
-            for (int t = tile - 1; t >= 0 && !done; t -= 8) {
-                unsigned v[8];
+            for (int t = tile - 1; t >= 0 && !done; t -= OS_WIN) {
+                unsigned v[OS_WIN];
 #pragma unroll
-                for (int w = 0; w < 8; ++w) v[w] = t - w >= 0 ? status[(size_t)(t - w) * RS_BINS + d] : (2u << 30);
+                for (int w = 0; w < OS_WIN; ++w) v[w] = t - w >= 0 ? status[(size_t)(t - w) * RS_BINS + d] : (2u << 30);
 #pragma unroll
-                for (int w = 0; w < 8; ++w) {
+                for (int w = 0; w < OS_WIN; ++w) {
                     if (done) break;
                     while ((v[w] >> 30) == 0u) { __nanosleep(20); v[w] = status[(size_t)(t - w) * RS_BINS + d]; }
                     excl += v[w] & OS_MASK;
