@@ -358,6 +358,28 @@ def test_three_steps_track_the_oracle(sph, oracle):
     np.testing.assert_allclose(info["stats"][:, 1:5], oo["stats"][:, 1:5], rtol=1e-9)
 
 
+@pytest.mark.parametrize("eos", ["isothermal", "polytropic"])
+def test_config0_100_steps_track_the_oracle(sph, oracle, eos):
+    """BASELINE.json configs[0] as stated: gaussian_sphere N = 5000, 100 iterations of the loop (all but the first are
+    replayed as a CUDA graph).  Measured: dt 1e-12, positions 4e-12 of the span after 100 steps."""
+    pos, vel, K, c, args = make_case(eos, "gaussian_sphere", 5000, R=5.38552341e16)
+    with sph.SphB200(5000, 50, eos, **args) as s:
+        s.upload(pos, vel, K, 0.0)
+        info = s.step(100)
+        p, v, Kend, t = s.download()
+    kw = oracle_kwargs(oracle, eos, c, K)
+    if eos == "isothermal":
+        kw["U_iso"] = c["U"]
+    oo = oracle.step(pos, vel, c["m"], 50, c["G"], c["theta"], 0.0, 100, nthreads=oracle.max_threads(), **kw)
+    np.testing.assert_allclose(info["dts"], oo["dts"], rtol=1e-9)
+    assert t == pytest.approx(oo["t"], rel=1e-9)
+    assert np.abs(p - oo["pos"]).max() < 1e-9 * np.abs(pos).max()
+    assert np.abs(v - oo["vel"]).max() < 1e-9 * np.abs(oo["vel"]).max()
+    np.testing.assert_allclose(info["stats"][:, 1:5], oo["stats"][:, 1:5], rtol=1e-9)
+    if eos == "polytropic":
+        np.testing.assert_allclose(Kend, oo["K"], rtol=1e-9)
+
+
 def test_density_at_points(sph, oracle):
     """HJL.density_plot (F/isothermal_hydroKDTree.jl:291-297): 1000 points on the x axis through the COM."""
     pos, vel, K, c, args = make_case("isothermal", "gaussian_sphere", 20_000, R=5.38552341e16)
