@@ -4,6 +4,8 @@ import sys
 
 import numpy as np
 
+os.environ.setdefault("SPH_B200_GRAPH_N", "0")   # plain launches: the phase timers printed below are not recorded in a graph replay
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import astrophysical_sph_b200.iniconds as ic  # noqa: E402
