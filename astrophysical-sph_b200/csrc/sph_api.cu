@@ -191,6 +191,18 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_SORT + 1], st));
     SPH_CUDA(h, sph_launch_tree(h));
     TRACE("sph_launch_tree done");
+    // Mass / rCOM of the cells are read by the walk only: the bottom-up sweep runs on the second stream beside the search
+    const bool ov = h->overlap && (!multi || h->nccl2 != nullptr);
+    cudaStream_t fs = ov ? h->stream2 : st;
+    if (ov) {
+        SPH_CUDA(h, cudaEventRecord(h->ev_tree, st));
+        SPH_CUDA(h, cudaStreamWaitEvent(fs, h->ev_tree, 0));
+    }
+    h->stream = fs;
+    cudaError_t ce = sph_launch_com(h);
+    h->stream = st;
+    SPH_CUDA(h, ce);
+    if (ov) SPH_CUDA(h, cudaEventRecord(h->ev_com, fs));
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_TREE + 1], st));
     SPH_CUDA(h, sph_launch_knn(h, t0, t1));
     TRACE("sph_launch_knn done");
@@ -208,8 +220,6 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     }
     SPH_CUDA(h, sph_launch_smoothing(h));
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_DENSITY + 1], st));
-    const bool ov = h->overlap && (!multi || h->nccl2 != nullptr);
-    cudaStream_t fs = ov ? h->stream2 : st;
     ncclComm_t fc = ov ? (ncclComm_t)h->nccl2 : comm;
     if (ov) {
         SPH_CUDA(h, cudaEventRecord(h->ev_fork, st));
@@ -257,6 +267,7 @@ int eval_internal(sph_handle *h, const double *pos, const double *vel, const dou
     SPH_CUDA(h, cudaEventRecord(h->fev[1], fs));
     if (ov) SPH_CUDA(h, cudaEventRecord(h->ev_join, fs));
     SPH_CUDA(h, cudaEventRecord(h->ev[PH_FORCE + 1], st));
+    if (ov) SPH_CUDA(h, cudaStreamWaitEvent(st, h->ev_com, 0));
     SPH_CUDA(h, sph_launch_walk(h));
     TRACE("sph_launch_walk done");
     if (multi) {
@@ -485,6 +496,8 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_com, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->fev[0])); CK(cudaEventCreate(&h->fev[1]));
     CK(cudaEventCreate(&h->dev[0])); CK(cudaEventCreate(&h->dev[1]));
     h->overlap = getenv("SPH_B200_NO_OVERLAP") == nullptr;
@@ -525,6 +538,8 @@ int sph_destroy(sph_handle *h) {
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_tree) cudaEventDestroy(h->ev_tree);
+    if (h->ev_com) cudaEventDestroy(h->ev_com);
     for (int i = 0; i < 2; ++i)
         if (h->fev[i]) cudaEventDestroy(h->fev[i]);
     for (int i = 0; i < 2; ++i)
@@ -854,6 +869,7 @@ int sph_density_at(sph_handle *h, const double *pts, int64_t M, double *rho_out)
     SPH_CUDA(h, sph_launch_domain_keys(h, h->pos));
     SPH_CUDA(h, sph_launch_permute(h, h->pos, h->vel, nullptr));
     SPH_CUDA(h, sph_launch_tree(h));
+    SPH_CUDA(h, sph_launch_com(h));           // not needed by the search; keeps the node table complete for sph_get_octree
     if (int rc = ensure_scratch(h, (size_t)M * (4 + (size_t)h->K) * 8)) return rc;
     double *d_pts = (double *)h->scratch, *d_rho = d_pts + 3 * M, *d_d2s = d_rho + M;
     cudaError_t e = cudaMemcpyAsync(d_pts, pts, (size_t)M * 3 * 8, cudaMemcpyHostToDevice, h->stream);

@@ -233,7 +233,7 @@ struct sph_handle {
     // the force kernel (+ its all-reduce) runs on a second stream, concurrently with the tree walk: both only need
     // the density/EOS results, and the latency-bound force kernel fills the issue slots the walk's tail leaves idle
     cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, fev[2]{}, dev[2]{};   // fev / dev: force and density phases on the stream they ran on
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_tree = nullptr, ev_com = nullptr, fev[2]{}, dev[2]{};   // fev / dev: force and density phases on the stream they ran on
     void *nccl2 = nullptr;  // communicator of stream2 (NCCL calls of one communicator must not run concurrently)
     bool overlap = true;
     bool ev_valid = false;
@@ -275,7 +275,8 @@ cudaError_t sph_exclusive_scan(const int *in, int *out, int64_t n, void *temp, s
 // ---- tree.cu -------------------------------------------------------------------------------------
 cudaError_t sph_launch_domain_keys(sph_handle *h, const double *pos);
 cudaError_t sph_launch_permute(sph_handle *h, const double *pos, const double *vel, const double *kent);
-cudaError_t sph_launch_tree(sph_handle *h);
+cudaError_t sph_launch_tree(sph_handle *h);      // node table (ranges, children, geometry): all the search needs
+cudaError_t sph_launch_com(sph_handle *h);       // Mass / rCOM bottom-up (setCOMs!): needed by the walk only
 
 // ---- knn.cu --------------------------------------------------------------------------------------
 cudaError_t sph_launch_knn(sph_handle *h, int64_t t0, int64_t t1);

@@ -312,7 +312,7 @@ cudaError_t sph_launch_tree(sph_handle *h) {
     cudaStream_t st = h->stream;
     SphTree &t = h->tree;
     const int64_t N = h->N;
-    sph_note(6);
+    sph_note(5);
     node_count_kernel<<<grid_for(N), TB, 0, st>>>(h->keys, h->klo, N, h->cnt, h->scal);
     cudaError_t e = sph_exclusive_scan(h->cnt, h->base, N, h->sort_tmp, h->sort_tmp_bytes, st);
     if (e != cudaSuccess) return e;
@@ -326,6 +326,15 @@ cudaError_t sph_launch_tree(sph_handle *h) {
     node_inverse_kernel<<<grid_for(t.cap), TB, 0, st>>>(t.dval_out, t.old_depth, h->scal, t.bfs_of_old, t.level_start);
     node_build_kernel<<<grid_for(t.cap), TB, 0, st>>>(h->keys, h->klo, N, h->cnt, h->base, t.dval_out, t.old_start,
                                                        t.old_depth, t.bfs_of_old, h->pos4, h->p.m, h->scal, t);
+    return cudaGetLastError();
+}
+
+// setCOMs! (F/gravOctree_Single.jl:183-211).  A launch of its own because only the walk reads Mass / rCOM: the
+// evaluation runs it on the second stream beside the neighbour search (sph_api.cu:eval_internal).
+cudaError_t sph_launch_com(sph_handle *h) {
+    cudaStream_t st = h->stream;
+    SphTree &t = h->tree;
+    sph_note(1);
     cudaMemsetAsync(t.arrive, 0, sizeof(int) * (size_t)t.cap, st);
     com_bottomup_kernel<<<grid_for(t.cap), TB, 0, st>>>(t, h->scal);
     return cudaGetLastError();
