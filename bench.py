@@ -242,6 +242,15 @@ def run_b200(args, rank, world, local_rank):
         s.eval_state()     # steps replayed as a CUDA graph record no phase timers: time one more evaluation
         tim = s.timings()
     value = n * args.steps / (ms * 1e-3)
+    per_rank = None
+    if dist is not None:
+        # the phases of every rank (the JSON line carries rank 0's as `phases_last_eval`): shows which rank the
+        # all-gathers wait for
+        mine = {k: round(tim[k + "_ms"], 3) for k in ("knn", "walk_kernel", "gravity", "density", "force", "total")}
+        mine["comm"] = round(tim.get("comm_ms") or 0.0, 3)
+        box = [None] * world
+        dist.all_gather_object(box, mine)
+        per_rank = box
 
     # ---- end to end through the public API with host buffers ("e2e"): every rank passes the full pinned arrays,
     # the library moves 1/world of them over PCIe per rank and exchanges the slices over NVLink; rank 0 reads the result
@@ -375,6 +384,8 @@ def run_b200(args, rank, world, local_rank):
     }
     if parity is not None:
         line["parity"] = parity
+    if per_rank is not None:
+        line["phases_per_rank"] = per_rank
     print(json.dumps(line), flush=True)
     s.close()
     if dist is not None:
