@@ -86,15 +86,65 @@ __device__ __forceinline__ double axis_dist_bits(double lo, double hi, double p)
     return __double2hiint(a) >= 0 ? a : bz;
 }
 
+// build-time experiments (tools/build_variants.sh): resident blocks of the pair walk, rare paths out of line
+#ifndef WALK_MINB
+#define WALK_MINB 8
+#endif
+#ifdef WALK_NOINLINE_C2
+#define C2_INLINE __noinline__
+#else
+#define C2_INLINE __forceinline__
+#endif
+
+// clause 2 of the acceptance rule evaluated with the reference's expression: h_i^2 / mindist^2(p_i, cell) < 0.25
+__device__ C2_INLINE bool clause2_exact(const double4 *__restrict__ nodeBC, int n, double px, double py, double pz, double hi2) {
+    const double4 B = nodeBC[2 * (int64_t)n];
+    const double4 C = nodeBC[2 * (int64_t)n + 1];
+    const double ex = axis_dist_bits(B.x, B.w, px), ey = axis_dist_bits(B.y, C.x, py), ez = axis_dist_bits(B.z, C.y, pz);
+    return quotient_less(hi2, sph_d2_exact(ex, ey, ez), 0.25);
+}
+
+// the reference's acceptance rule (:265) for one particle and one internal cell (both walks use it)
+__device__ __forceinline__ bool cell_accepted(const SphTree &t, int n, double s_sq, double radius, double d_sq,
+                                              double px, double py, double pz, double hi2, double h2x,
+                                              double theta_sq, double th_lo, double th_hi) {
+    // clause 1: s*s/d_sq < theta_sq
+    bool accept;
+    if (s_sq < d_sq * th_lo) accept = true;
+    else if (s_sq > d_sq * th_hi) accept = false;
+    else {
+        asm volatile("");   // see quotient_less
+        accept = s_sq / d_sq < theta_sq;
+    }
+    // clause 2: h_i*h_i / mind2 < 0.25, proven from d > radius + 2 h_i, else the reference's expression
+    if (accept) {
+        const double w = radius + h2x;
+        if (!(d_sq > w * w)) accept = clause2_exact(t.nodeBC, n, px, py, pz, hi2);
+    }
+    return accept;
+}
+
+// leaf = one particle j with smoothing length hj (:259-264): grad(PHI)/r and PHI per unit mass
+__device__ __forceinline__ void leaf_pair(double d_sq, double hi, double hj, double &gP, double &pot) {
+    const double hs = hi + hj;                           // 2 h_ij (:259)
+    if (d_sq > hs * hs) {                                // q > 2: Newtonian (:19-20); (2 h_ij)^2 is 4 h_ij^2 bit for bit
+        const double rinv = fast_rsqrt(d_sq);
+        gP = rinv * rinv * rinv;
+        pot = -rinv;
+    } else {
+        grav_pair(d_sq, hs / 2, gP, pot);
+    }
+}
+
 // Root children handled by block row y of a tile.  The children are ordered o = 0, 1, ..: o = 0 is the child that
 // CONTAINS the tile (its walk is by far the longest: the whole near field), o >= 1 the others in cyclic order; row y of
 // `rows` takes o = y, y + rows, ...  The hardware starts blocks in grid order, so every long work item begins before
 // any short one and the short ones fill the tail.
-__device__ __forceinline__ int walk_root_near(const double4 *__restrict__ W, int2 R, int64_t first_slot) {
+__device__ __forceinline__ int walk_root_near(const double4 *__restrict__ BC, int2 R, int64_t first_slot) {
     const int nch = R.y & 0xff;
     int near = 0;
     for (int c = 0; c < nch; ++c) {
-        const int2 rg = unpack_i2(W[GW_REC * (int64_t)(R.x + c) + 1].w);    // {nstart, ncount}
+        const int2 rg = unpack_i2(BC[2 * (int64_t)(R.x + c) + 1].w);        // {nstart, ncount}
         if (first_slot >= rg.x && first_slot < (int64_t)rg.x + rg.y) near = c;
     }
     return near;
@@ -140,7 +190,7 @@ __device__ __forceinline__ void walk_tile(int bx, int row, int rows, int4 *__res
     const int rnch = R.y & 0xff;
     if (row >= rnch) return;
     if (amask) {
-        const int near = walk_root_near(W, R, gtile * (GW_WARPS * 32));
+        const int near = walk_root_near(t.nodeBC, R, gtile * (GW_WARPS * 32));
         if (lane == 0) {
             int o = row;
             while (o + rows < rnch) o += rows;
@@ -172,15 +222,8 @@ __device__ __forceinline__ void walk_tile(int bx, int row, int rows, int4 *__res
                 // leaf = one particle j; A.w carries h_j, its mass is m.  The target's own leaf is skipped
                 // (the reference removes it from its parent's child list, :293-294).
                 if (mine && (int64_t)unpack_i2(V.z).x != s) {
-                    const double h_ij = (hi + A.w) / 2;                  // (:259)
                     double gP, pot;
-                    if (d_sq > 4.0 * (h_ij * h_ij)) {                    // q > 2: Newtonian (:19-20)
-                        const double rinv = fast_rsqrt(d_sq);
-                        gP = rinv * rinv * rinv;
-                        pot = -rinv;
-                    } else {
-                        grav_pair(d_sq, h_ij, gP, pot);
-                    }
+                    leaf_pair(d_sq, hi, A.w, gP, pot);
                     const double mg = m * gP;
                     gx += mg * dx; gy += mg * dy; gz += mg * dz;         // (:263)
                     ph += m * pot;                                       // (:264)
@@ -188,24 +231,7 @@ __device__ __forceinline__ void walk_tile(int bx, int row, int rows, int4 *__res
             } else {
                 bool open = false;
                 if (mine) {
-                    // clause 1: s*s/d_sq < theta_sq                                             (:265)
-                    bool accept;
-                    if (V.x < d_sq * th_lo) accept = true;
-                    else if (V.x > d_sq * th_hi) accept = false;
-                    else accept = V.x / d_sq < theta_sq;
-                    // clause 2: h_i*h_i / mind2 < 0.25, i.e. mindist > 2 h_i.  mindist >= d - radius proves it
-                    // for all but the cells within a few h_i; those evaluate the reference's expression.
-                    if (accept) {
-                        const double w = V.y + h2x;
-                        if (!(d_sq > w * w)) {
-                            const double4 B = t.nodeB[n];
-                            const double4 C = t.nodeC[n];
-                            const double ex = axis_dist(B.x, B.w, px), ey = axis_dist(B.y, C.x, py),
-                                         ez = axis_dist(B.z, C.y, pz);
-                            accept = quotient_less(hi2, sph_d2_exact(ex, ey, ez), 0.25);
-                        }
-                    }
-                    if (accept) {
+                    if (cell_accepted(t, n, V.x, V.y, d_sq, px, py, pz, hi2, h2x, theta_sq, th_lo, th_hi)) {
                         const double rinv = fast_rsqrt(d_sq);
                         const double f = A.w * (rinv * rinv * rinv);         // Mass / d^3  (:266-268)
                         gx += f * dx; gy += f * dy; gz += f * dz;
@@ -297,56 +323,6 @@ struct GpWarp {
     int q[GP_SOFT + SLACK];              // pairs: node | target lane << 27
 };
 
-// build-time experiments (tools/build_variants.sh): resident blocks of the pair walk, rare paths out of line
-#ifndef WALK_MINB
-#define WALK_MINB 8
-#endif
-#ifdef WALK_NOINLINE_C2
-#define C2_INLINE __noinline__
-#else
-#define C2_INLINE __forceinline__
-#endif
-
-// clause 2 of the acceptance rule evaluated with the reference's expression: h_i^2 / mindist^2(p_i, cell) < 0.25
-__device__ C2_INLINE bool clause2_exact(const double4 *__restrict__ nodeBC, int n, double px, double py, double pz, double hi2) {
-    const double4 B = nodeBC[2 * (int64_t)n];
-    const double4 C = nodeBC[2 * (int64_t)n + 1];
-    const double ex = axis_dist_bits(B.x, B.w, px), ey = axis_dist_bits(B.y, C.x, py), ez = axis_dist_bits(B.z, C.y, pz);
-    return quotient_less(hi2, sph_d2_exact(ex, ey, ez), 0.25);
-}
-
-// the reference's acceptance rule (:265) for one particle and one internal cell: same arithmetic as walk_kernel
-__device__ __forceinline__ bool cell_accepted(const SphTree &t, int n, double s_sq, double radius, double d_sq,
-                                              double px, double py, double pz, double hi2, double h2x,
-                                              double theta_sq, double th_lo, double th_hi) {
-    // clause 1: s*s/d_sq < theta_sq
-    bool accept;
-    if (s_sq < d_sq * th_lo) accept = true;
-    else if (s_sq > d_sq * th_hi) accept = false;
-    else {
-        asm volatile("");   // see quotient_less
-        accept = s_sq / d_sq < theta_sq;
-    }
-    // clause 2: h_i*h_i / mind2 < 0.25, proven from d > radius + 2 h_i, else the reference's expression
-    if (accept) {
-        const double w = radius + h2x;
-        if (!(d_sq > w * w)) accept = clause2_exact(t.nodeBC, n, px, py, pz, hi2);
-    }
-    return accept;
-}
-
-// leaf = one particle j with smoothing length hj (:259-264): grad(PHI)/r and PHI per unit mass
-__device__ __forceinline__ void leaf_pair(double d_sq, double hi, double hj, double &gP, double &pot) {
-    const double h_ij = (hi + hj) / 2;                   // (:259)
-    if (d_sq > 4.0 * (h_ij * h_ij)) {                    // q > 2: Newtonian (:19-20)
-        const double rinv = fast_rsqrt(d_sq);
-        gP = rinv * rinv * rinv;
-        pot = -rinv;
-    } else {
-        grav_pair(d_sq, h_ij, gP, pot);
-    }
-}
-
 template <bool COUNT, bool DEEP, int STACK, int QCAP>
 __device__ __forceinline__ void walk_pairs_tile(int bx, int row, int rows, GpWarp<STACK, QCAP - GP_SOFT> &sm, int64_t N, int nranks,
                                                 int rank, int64_t chunk, const double4 *__restrict__ pos4,
@@ -378,7 +354,7 @@ __device__ __forceinline__ void walk_pairs_tile(int bx, int row, int rows, GpWar
     sm.acc[lane] = make_double4(0.0, 0.0, 0.0, 0.0);
     int sp = 0;
     if (amask) {
-        const int near = walk_root_near(W, R, gtile * (GW_WARPS * 32));
+        const int near = walk_root_near(t.nodeBC, R, gtile * (GW_WARPS * 32));
         if (lane == 0) {
             int o = row;
             while (o + rows < rnch) o += rows;

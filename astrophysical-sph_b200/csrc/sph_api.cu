@@ -500,7 +500,7 @@ int sph_create(const sph_params *p, sph_handle **out) {
     CK(cudaEventCreateWithFlags(&h->ev_com, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->fev[0])); CK(cudaEventCreate(&h->fev[1]));
     CK(cudaEventCreate(&h->dev[0])); CK(cudaEventCreate(&h->dev[1]));
-    h->overlap = getenv("SPH_B200_NO_OVERLAP") == nullptr;
+    h->overlap = getenv("SPH_B200_NO_OVERLAP") == nullptr && !(h->p.flags & SPH_FLAG_SERIAL_PHASES);
     CK(cudaDeviceSynchronize());
 #undef CK
     *out = h;

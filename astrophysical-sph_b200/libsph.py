@@ -22,6 +22,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 ISOTHERMAL, POLYTROPIC = 0, 1
 FLAG_COUNT_VISITS = 1       # sph_params.flags: count the node visits of the tree walk (timings()["walk_visits"])
+FLAG_SERIAL_PHASES = 2      # sph_params.flags: density / force before the walk on one stream: timings() of every phase alone
 EOS_CODES = {"isothermal": ISOTHERMAL, "polytropic": POLYTROPIC}
 
 SPH_OK = 0

@@ -284,15 +284,22 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- node visits per particle of the walk (algorithmic flops of the dominant kernel): one counted evaluation on
     # a second handle (rank 0, one GPU's share is the same fraction of it)
+    # The same handle runs density / force BEFORE the walk on one stream (SPH_FLAG_SERIAL_PHASES): in the timed run they
+    # share the SMs with the walk on a second stream and their phase timers stretch over it, so the SPH-sum figures
+    # (`sph_sums`, `phases_alone`) come from here - each kernel alone, second (steady-state) evaluation.
     visits = None
+    alone = None
     fp64_peak = None
     if rank == 0:
         fp64_peak = libsph.measure_fp64_peak(dev)
     if world == 1:
-        s2 = SphB200(n, c["Kh"], eos, device=dev, flags=libsph.FLAG_COUNT_VISITS, **sph_args(eos, c))
+        s2 = SphB200(n, c["Kh"], eos, device=dev, flags=libsph.FLAG_COUNT_VISITS | libsph.FLAG_SERIAL_PHASES, **sph_args(eos, c))
         s2.upload(pos, vel, K, 0.0)
         s2.eval_state()
-        visits = s2.timings()["walk_visits"] / n
+        s2.eval_state()
+        t2 = s2.timings()
+        visits = t2["walk_visits"] / n
+        alone = {k: t2[k + "_ms"] for k in ("knn", "density", "force")}
         s2.close()
 
     if rank != 0:
@@ -319,7 +326,15 @@ def run_b200(args, rank, world, local_rank):
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get(dom)
-    sph_ms = phases["density"]["ms"] + phases["force"]["ms"]
+    phases_alone = None
+    if alone is not None:
+        phases_alone = {}
+        for k, t_ms in alone.items():
+            gbs = AB[k] * nt_targets / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+            phases_alone[k] = {"ms": round(t_ms, 4), "alg_bytes_per_particle": AB[k], "achieved_gbs": round(gbs, 2),
+                               "frac_hbm": round(gbs / peak, 5)}
+    sph_src = phases_alone if phases_alone is not None else phases
+    sph_ms = sph_src["density"]["ms"] + sph_src["force"]["ms"]
     sph_gbs = (AB["density"] + AB["force"]) * nt_targets / (sph_ms * 1e-3) / 1e9
     sph_tf = (FLOPS_SPH["density"] + FLOPS_SPH["force"]) * nt_targets / (sph_ms * 1e-3) / 1e12
 
@@ -376,8 +391,12 @@ def run_b200(args, rank, world, local_rank):
         "sph_sums": {"ms": round(sph_ms, 4), "achieved_gbs": round(sph_gbs, 2), "frac_hbm": round(sph_gbs / peak, 5),
                      "alg_bytes_per_particle": AB["density"] + AB["force"],
                      "achieved_tflops": round(sph_tf, 3), "frac_fp64": round(sph_tf / fp64_peak, 4),
-                     "alg_flops_per_particle": FLOPS_SPH["density"] + FLOPS_SPH["force"]},
+                     "alg_flops_per_particle": FLOPS_SPH["density"] + FLOPS_SPH["force"],
+                     "how": ("density + force phases each timed alone: second handle with SPH_FLAG_SERIAL_PHASES (`phases_alone`); "
+                             "in the timed run they execute on a second stream beside the walk (`phases_last_eval`)")
+                            if phases_alone is not None else "phases of the timed run (second stream, beside the walk)"},
         "phases_last_eval": phases,
+        "phases_alone": phases_alone,
         "knn_retries": tim.get("knn_retries"),
         "comm_ms_last_eval": tim.get("comm_ms"),
         "cpu_baseline": cpu,

@@ -68,6 +68,8 @@ typedef struct sph_params {
 
 /* sph_params.flags */
 #define SPH_FLAG_COUNT_VISITS 1 /* count the node visits of the tree walk (sph_timings.walk_visits); slows the walk */
+#define SPH_FLAG_SERIAL_PHASES 2 /* run density / force BEFORE the walk on one stream instead of beside it (same results):
+                                    sph_timings then holds the time of every phase alone (measurement; slower overall) */
 
 /* One row of the reference's stats matrix (F/isothermal_sim.jl:189-192) plus the step's dt. */
 typedef struct sph_step_info {
