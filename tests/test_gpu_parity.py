@@ -503,6 +503,26 @@ def test_run_simulation_writes_reference_files(sph, oracle, tmp_path):
     assert not np.any(np.array(stats[3:10]))
 
 
+def test_serial_phases_flag_changes_timings_only(sph):
+    """SPH_FLAG_SERIAL_PHASES (bench.py's `phases_alone`): density / force run before the walk on one stream instead of
+    beside it on the second one - the results are the same bit for bit (every sum has a fixed order), only the phase
+    timers differ."""
+    N = 20000
+    pos, vel, K, c, args = make_case("isothermal", "boss_bodenheimer", N, T=10)
+    res = []
+    for flags in (0, sph.FLAG_SERIAL_PHASES, sph.FLAG_SERIAL_PHASES | sph.FLAG_COUNT_VISITS):
+        with sph.SphB200(N, 50, "isothermal", flags=flags, **args) as s:
+            s.eval_acc(pos, vel)
+            out = s.eval_acc(pos, vel)
+            tm = s.timings()
+        res.append(out)
+        assert tm["density_ms"] > 0 and tm["force_ms"] > 0 and tm["gravity_ms"] > 0
+        assert (tm["walk_visits"] > 0) == bool(flags & sph.FLAG_COUNT_VISITS)
+    for out in res[1:]:
+        for k in ("acc", "rho", "h", "phi"):
+            assert np.array_equal(out[k], res[0][k]), k
+
+
 @pytest.mark.parametrize("env", ["SPH_B200_WALK_DFS=1", "SPH_B200_WALK_T=1", "SPH_B200_WALK_ROWS=1", "SPH_B200_NO_OVERLAP=1",
                                  "SPH_B200_KNN_SORT=1", "SPH_B200_NO_HINT=1", "SPH_B200_SPH_TILE=1", "SPH_B200_SPH_TILE=0",
                                  "SPH_B200_ECAP=8", "SPH_B200_WALK_FORCE_DEEP=1", "SPH_B200_GRAPH_N=0"])
