@@ -321,6 +321,7 @@ struct GpWarp {
     int2 stack[STACK];                   // {first child | nch << 27, lane mask}
     double4 acc[32];                     // sparse-path sums {gx, gy, gz, phi} of the warp's 32 targets
     int q[GP_SOFT + SLACK];              // pairs: node | target lane << 27
+    double2 rec[32];                     // the walk records of the popped cell's <= 8 children (64 B each)
 };
 
 template <bool COUNT, bool DEEP, int STACK, int QCAP>
@@ -468,10 +469,21 @@ __device__ __forceinline__ void walk_pairs_tile(int bx, int row, int rows, GpWar
             if (lane == 0) atomicOr(scal + SC_ERR, (unsigned long long)(DEEP ? ERRF_STACK2 : ERRF_STACK));
             break;
         }
+        // the records of all children (contiguous in BFS order, 64 B each) come into shared memory with ONE coalesced
+        // load per popped cell; the child loop then reads them with the short, fixed latency of shared memory instead
+        // of exposing a global-load latency per child (walk alone at N = 1e6: 5.76 -> 5.56 ms)
+#ifdef WALK_STAGE_PF
+        if (sp > 0) {   // the lines of the cell that is popped next unless this one pushes children
+            const int nx = sm.stack[sp - 1].x;
+            if (lane <= (nx >> 27) / 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(W + GW_REC * (int64_t)(nx & 0x7ffffff) + 4 * lane));
+        }
+#endif
+        if (lane < 4 * nch) sm.rec[lane] = reinterpret_cast<const double2 *>(W + GW_REC * (int64_t)first)[lane];
+        __syncwarp();
 #pragma unroll 1
         for (int c = 0; c < nch; ++c) {
             const int n = first + c;
-            const double4 A = W[GW_REC * (int64_t)n], V = W[GW_REC * (int64_t)n + 1];   // A = {rCOM, Mass | h_j}, V = {(2L)^2, radius, child info, range}
+            const double4 A = reinterpret_cast<const double4 *>(sm.rec)[2 * c], V = reinterpret_cast<const double4 *>(sm.rec)[2 * c + 1];   // A = {rCOM, Mass | h_j}, V = {(2L)^2, radius, child info, range}
             const double dx = px - A.x, dy = py - A.y, dz = pz - A.z;   // p_i - rCOM (:255)
             const double d_sq = sph_d2_exact(dx, dy, dz);                // (:256)
             if (COUNT && mine) ++visits;
