@@ -104,8 +104,9 @@ __device__ C2_INLINE bool clause2_exact(const double4 *__restrict__ nodeBC, int 
     return quotient_less(hi2, sph_d2_exact(ex, ey, ez), 0.25);
 }
 
-// the reference's acceptance rule (:265) for one particle and one internal cell (both walks use it)
-__device__ __forceinline__ bool cell_accepted(const SphTree &t, int n, double s_sq, double radius, double d_sq,
+// the reference's acceptance rule (:265) for one particle and one internal cell (both walks use it); bc[2 n], bc[2 n + 1]
+// is the cell's {box, ..} record
+__device__ __forceinline__ bool cell_accepted(const double4 *__restrict__ bc, int n, double s_sq, double radius, double d_sq,
                                               double px, double py, double pz, double hi2, double h2x,
                                               double theta_sq, double th_lo, double th_hi) {
     // clause 1: s*s/d_sq < theta_sq
@@ -119,7 +120,7 @@ __device__ __forceinline__ bool cell_accepted(const SphTree &t, int n, double s_
     // clause 2: h_i*h_i / mind2 < 0.25, proven from d > radius + 2 h_i, else the reference's expression
     if (accept) {
         const double w = radius + h2x;
-        if (!(d_sq > w * w)) accept = clause2_exact(t.nodeBC, n, px, py, pz, hi2);
+        if (!(d_sq > w * w)) accept = clause2_exact(bc, n, px, py, pz, hi2);
     }
     return accept;
 }
@@ -231,7 +232,7 @@ __device__ __forceinline__ void walk_tile(int bx, int row, int rows, int4 *__res
             } else {
                 bool open = false;
                 if (mine) {
-                    if (cell_accepted(t, n, V.x, V.y, d_sq, px, py, pz, hi2, h2x, theta_sq, th_lo, th_hi)) {
+                    if (cell_accepted(t.nodeBC, n, V.x, V.y, d_sq, px, py, pz, hi2, h2x, theta_sq, th_lo, th_hi)) {
                         const double rinv = fast_rsqrt(d_sq);
                         const double f = A.w * (rinv * rinv * rinv);         // Mass / d^3  (:266-268)
                         gx += f * dx; gy += f * dy; gz += f * dz;
@@ -402,7 +403,7 @@ __device__ __forceinline__ void walk_pairs_tile(int bx, int row, int rows, GpWar
                         fp = m * pot;                                        // (:264)
                         has = true;
                     }
-                } else if (cell_accepted(t, n, V.x, V.y, d_sq, tx, ty, tz, th * th, 2.0 * th * (1.0 + 1e-9), theta_sq, th_lo, th_hi)) {
+                } else if (cell_accepted(t.nodeBC, n, V.x, V.y, d_sq, tx, ty, tz, th * th, 2.0 * th * (1.0 + 1e-9), theta_sq, th_lo, th_hi)) {
                     const double rinv = fast_rsqrt(d_sq);
                     const double f = A.w * (rinv * rinv * rinv);             // Mass / d^3  (:266-268)
                     fx = f * dx; fy = f * dy; fz = f * dz;
@@ -472,12 +473,6 @@ __device__ __forceinline__ void walk_pairs_tile(int bx, int row, int rows, GpWar
         // the records of all children (contiguous in BFS order, 64 B each) come into shared memory with ONE coalesced
         // load per popped cell; the child loop then reads them with the short, fixed latency of shared memory instead
         // of exposing a global-load latency per child (walk alone at N = 1e6: 5.76 -> 5.56 ms)
-#ifdef WALK_STAGE_PF
-        if (sp > 0) {   // the lines of the cell that is popped next unless this one pushes children
-            const int nx = sm.stack[sp - 1].x;
-            if (lane <= (nx >> 27) / 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(W + GW_REC * (int64_t)(nx & 0x7ffffff) + 4 * lane));
-        }
-#endif
         if (lane < 4 * nch) sm.rec[lane] = reinterpret_cast<const double2 *>(W + GW_REC * (int64_t)first)[lane];
         __syncwarp();
 #pragma unroll 1
@@ -500,7 +495,7 @@ __device__ __forceinline__ void walk_pairs_tile(int bx, int row, int rows, GpWar
             } else {
                 bool open = false;
                 if (mine) {
-                    if (cell_accepted(t, n, V.x, V.y, d_sq, px, py, pz, hi2, h2x, theta_sq, th_lo, th_hi)) {
+                    if (cell_accepted(t.nodeBC, n, V.x, V.y, d_sq, px, py, pz, hi2, h2x, theta_sq, th_lo, th_hi)) {
                         const double rinv = fast_rsqrt(d_sq);
                         const double f = A.w * (rinv * rinv * rinv);         // Mass / d^3  (:266-268)
                         gx += f * dx; gy += f * dy; gz += f * dz;
@@ -631,7 +626,7 @@ cudaError_t sph_launch_walk(sph_handle *h) {
     // cells with <= sparse_t interested lanes are evaluated pair-wise (walk_pairs_kernel); 0 = never
     static const int sparse_t = [] {
         const char *e = getenv("SPH_B200_WALK_T");
-        const int v = e ? atoi(e) : 12;
+        const int v = e ? atoi(e) : 10;
         return v < 0 ? 0 : (v > GP_TMAX ? GP_TMAX : v);
     }();
     const double lo = th2 * (1.0 - 1e-15), hi = th2 * (1.0 + 1e-15);
