@@ -506,7 +506,7 @@ __device__ __forceinline__ void walk_pairs_tile(int bx, int row, int rows, GpWar
                 }
                 const unsigned om = __ballot_sync(0xffffffffu, open);
                 if (om) {
-                    if (lane == 0) sm.stack[sp] = make_int2(ci.x | ((ci.y & 0xff) << 27), (int)om);
+                    sm.stack[sp] = make_int2(ci.x | ((ci.y & 0xff) << 27), (int)om);   // every lane stores the same entry (no lane test)
                     ++sp;
                 }
             }
