@@ -29,8 +29,10 @@ struct Params          # mirrors `sph_params` (include/sph_b200.h), 88 bytes, C 
     beta::Float64
     U_iso::Float64
     device::Int32
-    flags::Int32
+    flags::Int32       # FLAG_* bits
 end
+const FLAG_COUNT_VISITS = Int32(1)    # count the node visits of the tree walk (timings: walk_visits)
+const FLAG_SERIAL_PHASES = Int32(2)   # density / force before the walk on one stream: phase timers of every kernel alone
 
 struct StepInfo        # mirrors `sph_step_info`
     dt::Float64
