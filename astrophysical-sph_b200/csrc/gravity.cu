@@ -609,13 +609,14 @@ cudaError_t sph_launch_walk(sph_handle *h) {
     double *out = h->walk_buf + (size_t)h->rank * 4 * h->walk_chunk;
     // block rows = work items per tile (the root's children are dealt to them): 8 - with more, shorter items the tail of
     // the launch stays short when the grid is only a wave or two of blocks (N = 1e5 on one GPU: 1.08 vs 1.50 ms with 2
-    // rows).  A rank that owns many waves of tiles (>= 4096 tiles = 3.5 waves of 148 x 8 blocks) takes ONE: the tail no
+    // rows).  A rank that owns many waves of tiles (>= 6144 tiles = 5 waves of 148 x 8 blocks; 4 rows from 4096 tiles, as
+    // measured earlier in the round) takes ONE: the tail no
     // longer matters, the kernel writes its sums straight into walk_buf, and the per-row partial sums (32 B per target
     // and row, written here, read by walk_reduce - the largest DRAM item of the launch) and the reduce kernel go away.
     // Evaluation at N = 1e6 beside the SPH kernels with 8 / 4 / 3 / 2 / 1 rows: 9.39 / 9.30 / 9.29 / 9.23 / 9.16 ms
     // (profiles/r02_walk_variants.txt, r4n / r4o).  SPH_B200_WALK_ROWS overrides (1..8).
     static const int rows_env = getenv("SPH_B200_WALK_ROWS") ? atoi(getenv("SPH_B200_WALK_ROWS")) : 0;
-    int rows = rows_env > 0 ? rows_env : (blocks >= 4096 ? 1 : 8);
+    int rows = rows_env > 0 ? rows_env : (blocks >= 6144 ? 1 : (blocks >= 4096 ? 4 : 8));
     rows = rows < 1 ? 1 : (rows > 8 ? 8 : rows);
     double *part = rows == 1 ? out : h->walk_part;
     const dim3 grid((unsigned)blocks, (unsigned)rows);
