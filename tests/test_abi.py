@@ -51,8 +51,9 @@ def test_struct_layouts_match_header(libsph):
     #include <stddef.h>
     #include "sph_b200.h"
     int main(void) {
-        printf("%zu %zu %zu %zu %zu %zu\n", sizeof(sph_params), offsetof(sph_params, m), offsetof(sph_params, device),
-               sizeof(sph_step_info), sizeof(sph_timings), offsetof(sph_params, U_iso));
+        printf("%zu %zu %zu %zu %zu %zu %d %d %zu\n", sizeof(sph_params), offsetof(sph_params, m), offsetof(sph_params, device),
+               sizeof(sph_step_info), sizeof(sph_timings), offsetof(sph_params, U_iso), SPH_FLAG_COUNT_VISITS,
+               SPH_FLAG_SERIAL_PHASES, offsetof(sph_params, flags));
         return 0;
     }"""
     with tempfile.TemporaryDirectory() as td:
@@ -63,7 +64,7 @@ def test_struct_layouts_match_header(libsph):
         vals = [int(x) for x in subprocess.check_output([exe]).split()]
     P = libsph.SphParams
     assert vals == [C.sizeof(P), P.m.offset, P.device.offset, C.sizeof(libsph.SphStepInfo), C.sizeof(libsph.SphTimings),
-                    P.U_iso.offset]
+                    P.U_iso.offset, libsph.FLAG_COUNT_VISITS, libsph.FLAG_SERIAL_PHASES, P.flags.offset]
 
 
 def test_no_device_fails_loudly(libsph):
